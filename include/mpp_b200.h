@@ -1,0 +1,199 @@
+/* mpp_b200.h -- C ABI of the B200-native Marked-Point-Process RJMCMC hot path.
+ *
+ * The reference (Ayana-Inria/MPP_CNN_RS_object_detection) is pure Python and has no native ABI; its boundary
+ * for this path is a set of Python call signatures.  This header is the C-ABI a
+ * binding for that path would target: every entry point names the reference interface it stands behind
+ * (paths relative to the reference root).  The Python facade in mpp_cnn_rs_object_detection_b200/ binds
+ * it with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  All array arguments are DEVICE pointers unless
+ *    the name ends in _host.  The caller (PyTorch) owns every buffer; the library owns only the opaque ctx
+ *    (cell lists, per-cell density sums, scratch) bound to one device and one cudaStream_t.
+ *  - Every call returns 0 on success or a negative mpp_status; mpp_last_error() gives the message of the
+ *    last failure on the calling thread.  Nothing throws across the boundary.
+ *  - A ctx is not thread-safe; different ctxs are independent.
+ *  - Calls are asynchronous on the ctx stream unless documented as synchronising.
+ */
+#ifndef MPP_B200_H
+#define MPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPP_ABI_VERSION 1
+#define MPP_CELL_SIZE 32      /* models/mpp/point_set/point_set.py:9,58  (cell = max(r_max, 32) px) */
+#define MPP_CELL_CAPACITY 32  /* object slots per cell == lanes of a warp */
+#define MPP_N_CLASSES 32      /* models/shape_net/shape_net_model.py:80-85 */
+#define MPP_MAX_TERMS 8       /* energy_setup_no_calibration.py:39-50 */
+#define MPP_NO_OBJECT 0xFFFFFFFFu
+
+typedef struct mpp_ctx mpp_ctx;
+
+typedef enum {
+    MPP_OK = 0,
+    MPP_ERR_INVALID = -1,      /* bad argument (python: AssertionError / ValueError) */
+    MPP_ERR_CUDA = -2,         /* CUDA runtime failure */
+    MPP_ERR_STATE = -3,        /* maps / model not set */
+    MPP_ERR_OUT_OF_BOUNDS = -4,/* object outside the support: point_set.py:99 assert */
+    MPP_ERR_CELL_FULL = -5,    /* more than MPP_CELL_CAPACITY objects in one 32x32 cell */
+    MPP_ERR_NEIGHBOURHOOD = -6,/* more than the scratch capacity of candidates around one perturbation */
+    MPP_ERR_NOT_FOUND = -7     /* removal of an unknown object: energy_point_set.py:88-100 KeyError */
+} mpp_status;
+
+typedef enum { MPP_PRECISION_FP32 = 0, MPP_PRECISION_FP64 = 1 } mpp_precision;
+typedef enum { MPP_SETUP_LEGACY = 0, MPP_SETUP_NO_CALIBRATION = 1 } mpp_setup;
+typedef enum {
+    MPP_COMB_RAW_SUM = 0,      /* energy_graph.py:132-133 (energy_combinator is None) */
+    MPP_COMB_HIERARCHICAL = 1, /* combination/hierarchical.py:21-32 */
+    MPP_COMB_LOGISTIC = 2,     /* combination/logistic.py:20-26 */
+    MPP_COMB_MANUAL_HIERARCHICAL = 3 /* combination/hierarchical.py:41-48 */
+} mpp_combinator;
+
+/* Energy model of one chain: what EnergySetup.make_energies builds (energy_setup_legacy.py:52-86,
+ * energy_setup_no_calibration.py:56-110) plus the combinator (custom_types/energy.py:8-11).
+ * Term order (columns of every energy-vector output):
+ *   legacy : Position, Shape, RectangleOverlap, ShapeAlignment, AreaPrior
+ *   nocalib: Position, Size, Ratio, Angle, OverlapPrior, AlignmentPrior, AreaPrior[, RatioPrior] */
+typedef struct {
+    int32_t setup;               /* mpp_setup */
+    int32_t combinator;          /* mpp_combinator */
+    int32_t ratio_prior;         /* nocalib only: append RatioPriorEnergy(target_ratio) */
+    int32_t rewarding;           /* ShapeAlignmentEnergy.rewarding (prior_energies.py:30) */
+    double pos_threshold;        /* PositionEnergy.threshold (data_energies.py:15) */
+    double remap_coef[3];        /* legacy: calibration.json param_dist_remap_coefs */
+    double remap_intercept[3];   /* legacy: param_dist_remap_intercepts */
+    double min_area, max_area;   /* AreaPriorEnergy (prior_energies.py:54-67) */
+    double target_ratio;         /* RatioPriorEnergy (prior_energies.py:71-78) */
+    double overlap_max_dist;     /* 32: energy_setup_legacy.py:70 */
+    double align_max_dist;       /* 16: energy_setup_legacy.py:75 */
+    /* combinator parameters.
+     *  hierarchical: w[0..1]=weights_data, w[2..4]=weights_prior, w[5..6]=data_prior_weights
+     *  logistic / manual: w[k] = weight of term k (term order above) */
+    double comb_w[MPP_MAX_TERMS];
+    double comb_bias;
+    double comb_threshold;       /* detection_threshold of the indicator */
+} mpp_model_params;
+
+/* Proposal-kernel parameters: make_kernels (rjmcmc_sampler/kernels/make_kernels.py:50-177). */
+typedef struct {
+    double p_kernel[8];          /* [UnifBirth, UnifDeath, DataBirth, DataDeath, GaussTrl, DataTrl, GaussTrf, DataTrf] */
+    double intensity;            /* Lambda = max(1, len(init_config)): sample_rjmcmc.py:68 */
+    double gauss_translation_sigma; /* 2   : make_kernels.py:124 */
+    int32_t data_translation_max_delta; /* 8 : make_kernels.py:130 */
+    int32_t reserved;
+    double gauss_transform_sigma;   /* 0.1 (fraction of each mark range): make_kernels.py:136 */
+} mpp_kernel_params;
+
+/* One recorded proposal == models/mpp/custom_types/perturbation.py:8-12 + the kernels' `data` dicts. */
+typedef struct {
+    int32_t kernel;              /* 0..7, order of make_kernels.py:88-144 */
+    int32_t rem_x, rem_y;        /* removed object (ignored when rem_uid == MPP_NO_OBJECT) */
+    uint32_t rem_uid;
+    int32_t add_x, add_y;        /* added object (ignored when add_uid == MPP_NO_OBJECT) */
+    uint32_t add_uid;
+    uint32_t add_cls;            /* packed classes size | ratio<<8 | angle<<16 (mappings.py:45-61, host float64) */
+    double add_size, add_ratio, add_angle;
+    double delta0, delta1;       /* gaussian translation delta (x,y) / gaussian transform delta */
+    int32_t param_id;            /* transform kernels: 0 size, 1 ratio, 2 angle */
+    int32_t new_class;           /* data-driven transform: drawn class */
+    double u;                    /* accept uniform: rng.random() of rjmcmc.py:113 */
+} mpp_proposal;
+
+/* What RJMCMC.step produced for one proposal (custom_types/rjmcmc.py:6-14). */
+typedef struct {
+    double delta_e;              /* EPointsSet.energy_delta */
+    double fwd, bwd;             /* Kernel.forward_probability / backward_probability */
+    double log_alpha;            /* rjmcmc.py:105-107 */
+    double temperature;
+    int32_t accepted;
+    int32_t n_after;
+} mpp_step_result;
+
+/* ---------------------------------------------------------------------------------------------- library */
+int mpp_abi_version(void);
+const char *mpp_last_error(void);
+/* sizeof of the ABI structs as compiled: 0 mpp_model_params, 1 mpp_kernel_params, 2 mpp_proposal, 3 mpp_step_result */
+int mpp_abi_struct_size(int which);
+
+/* ---------------------------------------------------------------------------------------------- context
+ * Stands behind PointsSet.__init__ (point_set.py:50-63) / EPointsSet.__init__ (energy_point_set.py:20-47):
+ * a uniform grid of 32-px cells over a (height, width) support.  `stream` is a cudaStream_t (0 = default). */
+int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precision, void *stream);
+int mpp_ctx_destroy(mpp_ctx *ctx);
+
+/* ImageWMaps.detection_map (H,W) f32 and param_dist_maps 3x(H,W,32) f32 (custom_types/image_w_maps.py:12-22).
+ * det_sum <= 0: the library reduces the map itself (float64); otherwise the caller passes
+ * float(np.sum(detection_map)) so that normalised densities match shape_samplers.py:87 bit for bit.
+ * Builds the per-cell density sums used by the data-driven birth sampler (utils/sampler2d.py:5-48). */
+int mpp_set_maps(mpp_ctx *ctx, const float *det, const float *marks, double det_sum);
+int mpp_set_model(mpp_ctx *ctx, const mpp_model_params *model_host);
+int mpp_set_kernels(mpp_ctx *ctx, const mpp_kernel_params *kernels_host);
+
+/* ---------------------------------------------------------------------------------------------- objects
+ * PointsSet.add / remove / __len__ / __iter__ (point_set.py:65-109), EPointsSet.add/remove (:72-78).
+ * xy [n][2] int32 (x=row, y=col), marks [n][3] float64 (size, ratio, angle), cls [n] packed classes or NULL
+ * (then classes are computed on device from the marks), uid [n] or NULL (then uids are assigned).
+ * out_handle [n] uint32 (cell*32 + slot) may be NULL.  Synchronises (reports CELL_FULL / OUT_OF_BOUNDS). */
+int mpp_add_objects(mpp_ctx *ctx, const int32_t *xy, const double *marks, const uint32_t *cls, const uint32_t *uid,
+                    int n, uint32_t *out_handle);
+int mpp_remove_objects(mpp_ctx *ctx, const uint32_t *handle, int n);
+int mpp_clear_objects(mpp_ctx *ctx);
+int mpp_num_objects(mpp_ctx *ctx, int *n_host);  /* synchronises */
+/* Cell-major enumeration (the order of PointsSetIterator, point_set.py:12-42).  Buffers hold `capacity`
+ * entries; any may be NULL.  *n_host receives the object count.  Synchronises. */
+int mpp_read_objects(mpp_ctx *ctx, int capacity, uint32_t *handle, int32_t *xy, double *marks, uint32_t *uid,
+                     int *n_host);
+
+/* ---------------------------------------------------------------------------------------------- energies
+ * EnergyGraph.compute_subset(return_vector=True) (energy_graph.py:108-137) for the objects named by `handle`
+ * (n of them): out_vectors [n][MPP_MAX_TERMS] (unused columns 0), out_combined [n] = combinator value of each
+ * object alone (both shipped combinators are sums over objects), out_totals [2] = {raw sum (energy_graph.py:105),
+ * combinator total}.  Any output may be NULL. */
+int mpp_energy_vectors(mpp_ctx *ctx, const uint32_t *handle, int n, double *out_vectors, double *out_combined,
+                       double *out_totals);
+
+/* EPointsSet.energy_delta (energy_point_set.py:83-100 -> energy_graph.py:139-225) for m independent
+ * perturbations against the current state (none is applied).  Only rem_* / add_* of each proposal are read.
+ * out_delta [m]. */
+int mpp_delta_batch(mpp_ctx *ctx, const mpp_proposal *props, int m, double *out_delta);
+
+/* ---------------------------------------------------------------------------------------------- chains
+ * Replays a recorded proposal stream strictly in order: RJMCMC.step (rjmcmc.py:83-164) with the kernel draws
+ * and the accept uniform taken from `props`.  Temperature starts at t0 and is multiplied by alpha_t after every
+ * step while > t_target (rjmcmc.py:158-159).  out [m]. */
+int mpp_replay(mpp_ctx *ctx, const mpp_proposal *props, int m, double t0, double alpha_t, double t_target,
+               mpp_step_result *out);
+
+/* Parallel sampler (new; replaces the sequential loop RJMCMC.run rjmcmc.py:172-181).  Each sweep visits the
+ * `stride`^2 colour classes of the cell grid once; every active cell performs `proposals_per_visit` local
+ * Metropolis-Hastings-Green proposals with Philox4x32-10 randomness keyed by (seed, cell, sweep).  Temperature
+ * is multiplied by alpha_t once per *sweep*.  counters_host[4] (may be NULL) receives
+ * {proposals, accepted, births accepted, deaths accepted} and synchronises. */
+int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stride, double t0, double alpha_t,
+                   double t_target, uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host);
+
+/* Draws n pixels from the normalised detection map (sample_point_2d, utils/sampler2d.py:39-46, as used by
+ * RectangleSampler.sample shape_samplers.py:90-94) and their three mark classes (shape_samplers.py:113-117):
+ * out [n][5] int32 = x, y, class_size, class_ratio, class_angle. */
+int mpp_sample_births(mpp_ctx *ctx, int n, uint64_t seed, int32_t *out);
+
+/* ---------------------------------------------------------------------------------------------- init
+ * naive_detection (sample_rjmcmc.py:23-35): threshold -> greedy distance NMS (utils/nms.py:68-109, 6 px) ->
+ * argmax marks; the surviving objects are inserted into the ctx.  *n_host receives their number. */
+int mpp_naive_init(mpp_ctx *ctx, double detection_threshold, double nms_distance, int *n_host);
+
+/* ---------------------------------------------------------------------------------------------- multi-GPU
+ * Scene split in row strips: objects whose row lies in [row_lo, row_hi) are packed as 8-double records
+ * (x, y, size, ratio, angle, cls, uid, 0) into `buf` (capacity records); *n_host receives the count.
+ * mpp_unpack_halo first deletes every object with row in [row_lo, row_hi) and then inserts the records. */
+int mpp_pack_rows(mpp_ctx *ctx, int row_lo, int row_hi, double *buf, int capacity, int *n_host);
+int mpp_unpack_rows(mpp_ctx *ctx, int row_lo, int row_hi, const double *buf, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPP_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI declared in include/mpp_b200.h.  There is no CPU fallback: if the CUDA library
+is missing or fails to load, importing a device object raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libmpp_b200.so")
+
+NO_OBJECT = 0xFFFFFFFF
+MAX_TERMS = 8
+PRECISION_FP32, PRECISION_FP64 = 0, 1
+SETUP_LEGACY, SETUP_NO_CALIBRATION = 0, 1
+COMB_RAW_SUM, COMB_HIERARCHICAL, COMB_LOGISTIC, COMB_MANUAL_HIERARCHICAL = 0, 1, 2, 3
+
+ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OUT_OF_BOUNDS, ERR_CELL_FULL, ERR_NEIGHBOURHOOD, ERR_NOT_FOUND = -1, -2, -3, -4, -5, -6, -7
+
+
+class ModelParams(C.Structure):
+    _fields_ = [("setup", C.c_int32), ("combinator", C.c_int32), ("ratio_prior", C.c_int32), ("rewarding", C.c_int32),
+                ("pos_threshold", C.c_double), ("remap_coef", C.c_double * 3), ("remap_intercept", C.c_double * 3),
+                ("min_area", C.c_double), ("max_area", C.c_double), ("target_ratio", C.c_double),
+                ("overlap_max_dist", C.c_double), ("align_max_dist", C.c_double), ("comb_w", C.c_double * MAX_TERMS),
+                ("comb_bias", C.c_double), ("comb_threshold", C.c_double)]
+
+
+class KernelParams(C.Structure):
+    _fields_ = [("p_kernel", C.c_double * 8), ("intensity", C.c_double), ("gauss_translation_sigma", C.c_double),
+                ("data_translation_max_delta", C.c_int32), ("reserved", C.c_int32), ("gauss_transform_sigma", C.c_double)]
+
+
+# numpy mirrors of mpp_proposal / mpp_step_result (C layout, natural alignment)
+PROPOSAL_DTYPE = np.dtype([("kernel", "<i4"), ("rem_x", "<i4"), ("rem_y", "<i4"), ("rem_uid", "<u4"), ("add_x", "<i4"),
+                           ("add_y", "<i4"), ("add_uid", "<u4"), ("add_cls", "<u4"), ("add_size", "<f8"),
+                           ("add_ratio", "<f8"), ("add_angle", "<f8"), ("delta0", "<f8"), ("delta1", "<f8"),
+                           ("param_id", "<i4"), ("new_class", "<i4"), ("u", "<f8")], align=True)
+STEP_RESULT_DTYPE = np.dtype([("delta_e", "<f8"), ("fwd", "<f8"), ("bwd", "<f8"), ("log_alpha", "<f8"),
+                              ("temperature", "<f8"), ("accepted", "<i4"), ("n_after", "<i4")], align=True)
+
+# every symbol include/mpp_b200.h declares
+SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_create", "mpp_ctx_destroy", "mpp_set_maps",
+           "mpp_set_model", "mpp_set_kernels", "mpp_add_objects", "mpp_remove_objects", "mpp_clear_objects",
+           "mpp_num_objects", "mpp_read_objects", "mpp_energy_vectors", "mpp_delta_batch", "mpp_replay",
+           "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows"]
+
+_lib = None
+
+
+class MPPError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[mpp_b200 {code}] {message}")
+        self.code = code
+
+
+def load():
+    """Loads libmpp_b200.so (built in-tree by build.py).  Raises if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -m mpp_cnn_rs_object_detection_b200.build` "
+                           f"(the MPP sampler has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f64, u64 = C.c_void_p, C.c_int, C.c_double, C.c_uint64
+    for name in SYMBOLS:
+        getattr(lib, name).restype = C.c_int
+    lib.mpp_last_error.restype = C.c_char_p
+    lib.mpp_abi_struct_size.argtypes = [i32]
+    lib.mpp_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, vp]
+    lib.mpp_ctx_destroy.argtypes = [vp]
+    lib.mpp_set_maps.argtypes = [vp, vp, vp, f64]
+    lib.mpp_set_model.argtypes = [vp, C.POINTER(ModelParams)]
+    lib.mpp_set_kernels.argtypes = [vp, C.POINTER(KernelParams)]
+    lib.mpp_add_objects.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    lib.mpp_remove_objects.argtypes = [vp, vp, i32]
+    lib.mpp_clear_objects.argtypes = [vp]
+    lib.mpp_num_objects.argtypes = [vp, C.POINTER(i32)]
+    lib.mpp_read_objects.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(i32)]
+    lib.mpp_energy_vectors.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.mpp_delta_batch.argtypes = [vp, vp, i32, vp]
+    lib.mpp_replay.argtypes = [vp, vp, i32, f64, f64, f64, vp]
+    lib.mpp_run_sweeps.argtypes = [vp, i32, i32, i32, f64, f64, f64, u64, u64, C.POINTER(C.c_ulonglong)]
+    lib.mpp_sample_births.argtypes = [vp, i32, u64, vp]
+    lib.mpp_naive_init.argtypes = [vp, f64, f64, C.POINTER(i32)]
+    lib.mpp_pack_rows.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    lib.mpp_unpack_rows.argtypes = [vp, i32, i32, vp, i32]
+    if lib.mpp_abi_version() != 1:
+        raise RuntimeError("libmpp_b200.so ABI version mismatch")
+    sizes = [C.sizeof(ModelParams), C.sizeof(KernelParams), PROPOSAL_DTYPE.itemsize, STEP_RESULT_DTYPE.itemsize]
+    for which, sz in enumerate(sizes):
+        if lib.mpp_abi_struct_size(which) != sz:
+            raise RuntimeError(f"ABI struct {which} size mismatch: C {lib.mpp_abi_struct_size(which)} vs python {sz}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MPPError(rc, load().mpp_last_error().decode())

@@ -1,0 +1,925 @@
+// B200-native Marked-Point-Process RJMCMC hot path: kernels + the C ABI of include/mpp_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mpp_device.cuh"
+#include "mpp_proposals.cuh"
+
+// ================================================================================================ host ctx
+struct mpp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int precision = 0;
+    int H = 0, W = 0, nx = 0, ny = 0, ncell = 0;
+    uint32_t *d_mask = nullptr;
+    void *d_recs = nullptr;
+    double *d_cell_cdf = nullptr;
+    int *d_scan = nullptr;              // [ncell + 1] exclusive prefix of per-cell populations
+    int *d_nobj = nullptr;
+    uint32_t *d_next_uid = nullptr;
+    uint32_t *d_err = nullptr;
+    unsigned long long *d_counters = nullptr;
+    unsigned char *d_nms_state = nullptr;  // [H*W] naive-init scratch, allocated on first use
+    const float *det = nullptr;
+    const float *marks = nullptr;
+    float det_sum = 0.f;
+    bool maps_set = false, model_set = false, kernels_set = false;
+    ModelDev m;
+    KernDev k;
+    int *h_pinned = nullptr;            // small pinned read-back area (16 x 8 bytes)
+};
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(MPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+template <typename R>
+static Ctx<R> device_view(const mpp_ctx *h) {
+    Ctx<R> c;
+    c.H = h->H; c.W = h->W; c.nx = h->nx; c.ny = h->ny; c.ncell = h->ncell;
+    c.mask = h->d_mask;
+    c.recs = reinterpret_cast<Rec<R> *>(h->d_recs);
+    c.det = h->det; c.marks = h->marks; c.det_sum = h->det_sum;
+    c.cell_cdf = h->d_cell_cdf;
+    c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
+    c.m = h->m; c.k = h->k;
+    return c;
+}
+
+#define DISPATCH(h, CALL)                                         \
+    do {                                                          \
+        if ((h)->precision == MPP_PRECISION_FP64) { typedef double R; CALL; } \
+        else { typedef float R; CALL; }                           \
+    } while (0)
+
+static int check_device_errors(mpp_ctx *h) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_pinned, h->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const uint32_t f = *reinterpret_cast<uint32_t *>(h->h_pinned);
+    if (!f) return MPP_OK;
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
+    if (f & ERRF_OUT_OF_BOUNDS) return fail(MPP_ERR_OUT_OF_BOUNDS, "object outside the support (point_set.py:99)");
+    if (f & ERRF_NOT_FOUND) return fail(MPP_ERR_NOT_FOUND, "removal of an object that is not in the set");
+    if (f & ERRF_CELL_FULL) return fail(MPP_ERR_CELL_FULL, "more than 32 objects in one 32x32 cell");
+    return fail(MPP_ERR_NEIGHBOURHOOD, "more than MPP_KMAX objects around one perturbation");
+}
+
+// ================================================================================================ kernels
+// ---- K5a: per-cell detection mass (warp per cell) -------------------------------------------------
+__global__ void k_cell_mass(const float *__restrict__ det, int H, int W, int ny, int ncell, double *__restrict__ mass) {
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= ncell) return;
+    const int x = (cell / ny) * 32 + lane, y0 = (cell % ny) * 32;
+    double s = 0.0;
+    if (x < H) {
+        const float *row = det + (size_t)x * W + y0;
+        const int wy = min(32, W - y0);
+        for (int j = 0; j < wy; ++j) s += (double)__ldg(row + j);
+    }
+    s = warp_sum(s);
+    if (lane == 0) mass[cell] = s;
+}
+
+// single-block inclusive scan of doubles in place (ncell <= a few 1e5)
+__global__ void k_scan_double(double *v, int n) {
+    __shared__ double part[1024];
+    const int t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = t * per, e = min(n, b + per);
+    double s = 0.0;
+    for (int i = b; i < e; ++i) s += v[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) { double a = 0.0; for (int i = 0; i < (int)blockDim.x; ++i) { double x = part[i]; part[i] = a; a += x; } }
+    __syncthreads();
+    double a = part[t];
+    for (int i = b; i < e; ++i) { a += v[i]; v[i] = a; }
+}
+
+// ---- K1: objects ----------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_add_objects(Ctx<R> c, const int32_t *__restrict__ xy, const double *__restrict__ marks,
+                              const uint32_t *__restrict__ cls, const uint32_t *__restrict__ uid, int n,
+                              uint32_t *__restrict__ out_handle) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (out_handle) out_handle[i] = MPP_NO_OBJECT;
+    if (x < 0 || y < 0 || x >= c.H || y >= c.W) { atomicOr(c.err, ERRF_OUT_OF_BOUNDS); return; }
+    const R size = (R)marks[3 * i], ratio = (R)marks[3 * i + 1], angle = (R)marks[3 * i + 2];
+    const uint32_t pc = cls ? cls[i] : pack_cls(value_to_class<R>(0, size), value_to_class<R>(1, ratio), value_to_class<R>(2, angle));
+    const uint32_t id = uid ? uid[i] : atomicAdd(c.next_uid, 1u);
+    const Rec<R> r = make_rec(c, x, y, size, ratio, angle, pc, id);
+    const int cell = cell_of(c, x, y);
+    for (;;) {
+        const uint32_t msk = atomicOr(c.mask + cell, 0u);
+        if (msk == 0xffffffffu) { atomicOr(c.err, ERRF_CELL_FULL); return; }
+        const int slot = __ffs(~msk) - 1;
+        const uint32_t old = atomicOr(c.mask + cell, 1u << slot);
+        if (!(old & (1u << slot))) {
+            store_rec(c.recs + (size_t)cell * 32 + slot, r);
+            if (out_handle) out_handle[i] = (uint32_t)cell * 32u + slot;
+            atomicAdd(c.n_objects, 1);
+            return;
+        }
+    }
+}
+
+template <typename R>
+__global__ void k_remove_objects(Ctx<R> c, const uint32_t *__restrict__ handle, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t h = handle[i];
+    if ((h >> 5) >= (uint32_t)c.ncell) { atomicOr(c.err, ERRF_NOT_FOUND); return; }
+    const uint32_t bit = 1u << (h & 31);
+    const uint32_t old = atomicAnd(c.mask + (h >> 5), ~bit);
+    if (old & bit) atomicSub(c.n_objects, 1);
+    else atomicOr(c.err, ERRF_NOT_FOUND);
+}
+
+// single-block exclusive scan of the per-cell populations -> scan[0..ncell]
+__global__ void k_scan_population(const uint32_t *__restrict__ mask, int ncell, int *__restrict__ scan) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x, per = (ncell + blockDim.x - 1) / blockDim.x;
+    const int b = min(ncell, t * per), e = min(ncell, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += __popc(mask[i]);
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) { int a = 0; for (int i = 0; i < (int)blockDim.x; ++i) { int x = part[i]; part[i] = a; a += x; } scan[ncell] = a; }
+    __syncthreads();
+    int a = part[t];
+    for (int i = b; i < e; ++i) { scan[i] = a; a += __popc(mask[i]); }
+}
+
+template <typename R>
+__global__ void k_read_objects(Ctx<R> c, const int *__restrict__ scan, int capacity, uint32_t *handle, int32_t *xy,
+                               double *marks, uint32_t *uid) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c.ncell) return;
+    uint32_t msk = c.mask[cell];
+    int pos = scan[cell];
+    while (msk) {
+        const int slot = __ffs(msk) - 1;
+        msk &= msk - 1;
+        if (pos < capacity) {
+            const Rec<R> r = load_rec(c.recs + (size_t)cell * 32 + slot);
+            if (handle) handle[pos] = (uint32_t)cell * 32u + slot;
+            if (xy) { xy[2 * pos] = r.x; xy[2 * pos + 1] = r.y; }
+            if (marks) { marks[3 * pos] = (double)r.size; marks[3 * pos + 1] = (double)r.ratio; marks[3 * pos + 2] = (double)r.angle; }
+            if (uid) uid[pos] = r.uid;
+        }
+        ++pos;
+    }
+}
+
+// ---- K2-K4: per-object energy vectors (warp per object) ---------------------------------------------
+template <typename R>
+__global__ void k_energy_vectors(Ctx<R> c, const uint32_t *__restrict__ handle, int n, double *__restrict__ out_vectors,
+                                 double *__restrict__ out_combined) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Scratch<R> &s = reinterpret_cast<Scratch<R> *>(smem)[wib];
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (i >= n) return;
+    const uint32_t h = handle[i];
+    const bool ok = (h >> 5) < (uint32_t)c.ncell && ((c.mask[h >> 5] >> (h & 31)) & 1u);
+    if (!ok) {
+        if (lane == 0) {
+            atomicOr(c.err, ERRF_NOT_FOUND);
+            if (out_combined) out_combined[i] = 0.0;
+        }
+        return;
+    }
+    const Rec<R> u = load_rec(c.recs + h);
+    const Terms<R> t = warp_object_terms(c, s, h, u, lane);
+    if (lane == 0) {
+        R v[MPP_MAX_TERMS];
+        term_vector(c.m, t, v);
+        if (out_vectors)
+            for (int k = 0; k < MPP_MAX_TERMS; ++k) out_vectors[(size_t)i * MPP_MAX_TERMS + k] = k < c.m.n_terms ? (double)v[k] : 0.0;
+        if (out_combined) out_combined[i] = (double)combine(c.m, t);
+    }
+}
+
+// deterministic totals: {sum of all vector entries, sum of combined}
+__global__ void k_totals(const double *__restrict__ vectors, const double *__restrict__ combined, int n, double *__restrict__ out) {
+    __shared__ double pa[256], pb[256];
+    const int t = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int i = t; i < n; i += blockDim.x) {
+        if (vectors) for (int k = 0; k < MPP_MAX_TERMS; ++k) a += vectors[(size_t)i * MPP_MAX_TERMS + k];
+        if (combined) b += combined[i];
+    }
+    pa[t] = a; pb[t] = b;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (t < o) { pa[t] += pa[t + o]; pb[t] += pb[t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) { out[0] = pa[0]; out[1] = pb[0]; }
+}
+
+// ---- K3: batch of independent perturbations (warp per perturbation) ---------------------------------
+template <typename R>
+__device__ __forceinline__ bool resolve_proposal(const Ctx<R> &c, const mpp_proposal &p, int lane, bool *has_rem,
+                                                 uint32_t *rem_handle, Rec<R> *rem, bool *has_add, Rec<R> *add) {
+    *has_rem = p.rem_uid != MPP_NO_OBJECT;
+    *has_add = p.add_uid != MPP_NO_OBJECT;
+    *rem_handle = MPP_NO_OBJECT;
+    if (*has_rem) {
+        *rem_handle = find_by_uid(c, p.rem_x, p.rem_y, p.rem_uid, lane);
+        if (*rem_handle == MPP_NO_OBJECT) { if (lane == 0) atomicOr(c.err, ERRF_NOT_FOUND); return false; }
+        *rem = load_rec(c.recs + *rem_handle);
+    }
+    if (*has_add) {
+        if (p.add_x < 0 || p.add_y < 0 || p.add_x >= c.H || p.add_y >= c.W) { if (lane == 0) atomicOr(c.err, ERRF_OUT_OF_BOUNDS); return false; }
+        *add = make_rec(c, p.add_x, p.add_y, (R)p.add_size, (R)p.add_ratio, (R)p.add_angle, p.add_cls, p.add_uid);
+    }
+    return true;
+}
+
+template <typename R>
+__global__ void k_delta_batch(Ctx<R> c, const mpp_proposal *__restrict__ props, int m, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Scratch<R> &s = reinterpret_cast<Scratch<R> *>(smem)[wib];
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (i >= m) return;
+    const mpp_proposal p = props[i];
+    bool has_rem, has_add;
+    uint32_t rh;
+    Rec<R> rem, add;
+    if (!resolve_proposal(c, p, lane, &has_rem, &rh, &rem, &has_add, &add)) { if (lane == 0) out[i] = 0.0; return; }
+    const R d = warp_delta(c, s, has_rem, rh, rem, has_add, add, lane);
+    if (lane == 0) out[i] = (double)d;
+}
+
+// ---- K7: sequential replay of a recorded proposal stream (one warp) --------------------------------
+template <typename R>
+__global__ void k_replay(Ctx<R> c, const mpp_proposal *__restrict__ props, int m, double t0, double alpha_t,
+                         double t_target, mpp_step_result *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Scratch<R> &s = *reinterpret_cast<Scratch<R> *>(smem);
+    const int lane = threadIdx.x & 31;
+    int n = __ldcg(c.n_objects);
+    double temp = t0;
+    for (int step = 0; step < m; ++step) {
+        const mpp_proposal p = props[step];
+        bool has_rem, has_add;
+        uint32_t rh;
+        Rec<R> rem, add;
+        mpp_step_result res;
+        res.delta_e = 0; res.fwd = 0; res.bwd = 0; res.log_alpha = 0; res.temperature = temp; res.accepted = -1; res.n_after = n;
+        if (resolve_proposal(c, p, lane, &has_rem, &rh, &rem, &has_add, &add)) {
+            const R d = warp_delta(c, s, has_rem, rh, rem, has_add, add, lane);
+            double fwd, bwd;
+            proposal_probs(c, p.kernel, has_rem, rem, has_add, add, p.delta0, p.delta1, p.param_id, p.new_class, (double)n,
+                           c.k.intensity, lane, &fwd, &bwd);
+            const double la = (-(double)d / temp) + log(bwd + MPP_EPS) - log(fwd + MPP_EPS);  // rjmcmc.py:105-107
+            const bool acc = log(p.u + MPP_EPS) < la;                                         // rjmcmc.py:113
+            if (acc) {  // EPointsSet.apply_perturbation: removal first (energy_point_set.py:123-141)
+                if (has_rem) { erase_handle(c, rh, lane); --n; }
+                __syncwarp();
+                if (has_add) { insert_rec(c, add, lane); ++n; }
+                __syncwarp();
+            }
+            res.delta_e = (double)d; res.fwd = fwd; res.bwd = bwd; res.log_alpha = la; res.accepted = acc ? 1 : 0; res.n_after = n;
+        }
+        if (lane == 0) out[step] = res;
+        if (temp > t_target) temp *= alpha_t;  // rjmcmc.py:158-159
+    }
+    if (lane == 0) *c.n_objects = n;
+}
+
+// ---- K5 test entry: draw births from the data-driven sampler ---------------------------------------
+template <typename R>
+__global__ void k_sample_births(Ctx<R> c, int n, uint64_t seed, int32_t *__restrict__ out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    Philox rng(seed, (uint32_t)i, 0x5a17u, 0);
+    const uint4 a = rng.next(), b = rng.next();
+    int x, y;
+    sample_birth_pixel(c, u01(a.x, a.y), u01f(a.z), u01f(a.w), lane, &x, &y);
+    const int c0 = sample_mark_class(c, 0, x, y, u01f(b.x), lane);
+    const int c1 = sample_mark_class(c, 1, x, y, u01f(b.y), lane);
+    const int c2 = sample_mark_class(c, 2, x, y, u01f(b.z), lane);
+    if (lane == 0) { out[5 * i] = x; out[5 * i + 1] = y; out[5 * i + 2] = c0; out[5 * i + 3] = c1; out[5 * i + 4] = c2; }
+}
+
+// ---- K6: parallel sweep over one colour class (warp per active cell) -------------------------------
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, uint32_t cc, uint32_t d, double *n0, double *n1) {
+    const double u1 = u01(a, b), u2 = u01(cc, d);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    *n0 = r * cs; *n1 = r * sn;
+}
+
+template <typename R>
+__global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj, int per_visit, double temp,
+                        uint64_t seed, uint64_t sweep_id) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Scratch<R> &s = reinterpret_cast<Scratch<R> *>(smem)[wib];
+    const int a = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (a >= n_ai * n_aj) return;
+    const int i = ci + stride * (a / n_aj), j = cj + stride * (a % n_aj);
+    const int cell = j + i * c.ny;
+    const int x0 = i * 32, x1 = min(x0 + 32, c.H), y0 = j * 32, y1 = min(y0 + 32, c.W);
+    const int wx = x1 - x0, wy = y1 - y0;
+    const bool in_cell_moves = stride < 4;  // stride 3: moves must stay in the cell; stride >= 4: |move| <= 16 px
+    const double q_unif = ((double)wx * (double)wy) / ((double)c.H * (double)c.W);
+    const double cell_mass = c.cell_cdf[cell] - (cell > 0 ? c.cell_cdf[cell - 1] : 0.0);
+    const double q_data = cell_mass / c.cell_cdf[c.ncell - 1];
+    Philox rng(seed, (uint32_t)cell, (uint32_t)sweep_id, (uint32_t)(sweep_id >> 32));
+    unsigned n_acc = 0, n_birth = 0, n_death = 0;
+    int dn = 0;
+    double cdf[8];
+    { double acc = 0; for (int k = 0; k < 8; ++k) { acc += c.k.p[k]; cdf[k] = acc; } }
+
+    for (int it = 0; it < per_visit; ++it) {
+        const uint4 r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
+        const uint32_t msk = __ldcg(c.mask + cell);
+        const int nc = __popc(msk);
+        int kernel = 7;
+        { const double uk = u01(r0.x, r0.y) * cdf[7]; for (int k = 6; k >= 0; --k) if (uk < cdf[k]) kernel = k; }
+        bool has_rem = false, has_add = false, valid = true;
+        uint32_t rh = MPP_NO_OBJECT;
+        Rec<R> rem, add;
+        double d0 = 0, d1 = 0, lambda = 1.0;
+        int param_id = 0, new_class = 0;
+        if (kernel >= 1 && kernel != 2 && nc > 0) {  // kernels that pick an existing object uniformly in the cell
+            const int pick = min(nc - 1, (int)(u01f(r0.z) * (float)nc));
+            rh = (uint32_t)cell * 32u + __fns(msk, 0, pick + 1);
+            rem = load_rec(c.recs + rh);
+            has_rem = true;
+        }
+        switch (kernel) {
+        case 0: {  // UniformRectangleSampler.sample shape_samplers.py:136-141, restricted to the cell
+            const int x = x0 + min(wx - 1, (int)(u01f(r0.z) * (float)wx)), y = y0 + min(wy - 1, (int)(u01f(r0.w) * (float)wy));
+            const R size = (R)(u01(r1.x, r1.y) * 32.0), ratio = (R)u01(r1.z, r1.w), angle = (R)(u01(r2.x, r2.y) * 3.14159265358979323846);
+            add = make_rec(c, x, y, size, ratio, angle,
+                           pack_cls(value_to_class<R>(0, size), value_to_class<R>(1, ratio), value_to_class<R>(2, angle)), 0u);
+            has_add = true;
+            lambda = c.k.intensity * q_unif;
+            break;
+        }
+        case 2: {  // RectangleSampler.sample shape_samplers.py:90-98, restricted to the cell
+            if (!(cell_mass > 0.0)) { valid = false; break; }
+            int x, y;
+            sample_window(c, x0, x1, y0, y1, u01f(r0.z), u01f(r0.w), lane, &x, &y, nullptr);
+            const int c0 = sample_mark_class(c, 0, x, y, u01f(r1.x), lane);
+            const int c1 = sample_mark_class(c, 1, x, y, u01f(r1.y), lane);
+            const int c2 = sample_mark_class(c, 2, x, y, u01f(r1.z), lane);
+            add = make_rec(c, x, y, mark_edge<R>(0, c0), mark_edge<R>(1, c1), mark_edge<R>(2, c2), pack_cls(c0, c1, c2), 0u);
+            has_add = true;
+            lambda = c.k.intensity * q_data;
+            break;
+        }
+        case 1: lambda = c.k.intensity * q_unif; break;
+        case 3: lambda = c.k.intensity * q_data; if (has_rem && !(cell_mass > 0.0)) valid = false; break;
+        case 4: if (has_rem) {  // GaussianTranslationKernel.sample_perturbation transform_kernels.py:24-36
+            box_muller(r1.x, r1.y, r1.z, r1.w, &d0, &d1);
+            d0 *= c.k.trl_sigma; d1 *= c.k.trl_sigma;
+            int nx_ = (int)((double)rem.x + d0), ny_ = (int)((double)rem.y + d1);  // astype(int): truncation
+            nx_ = min(max(nx_, 0), c.H - 1); ny_ = min(max(ny_, 0), c.W - 1);
+            add = rem; add.x = nx_; add.y = ny_;
+            has_add = true;
+        } break;
+        case 5: if (has_rem) {  // DataDrivenTranslationKernel.sample_perturbation :77-89
+            const int md = c.k.trl_max_delta;
+            int x, y;
+            sample_window(c, max(0, rem.x - md), min(rem.x + md + 1, c.H), max(0, rem.y - md), min(rem.y + md + 1, c.W),
+                          u01f(r1.x), u01f(r1.y), lane, &x, &y, nullptr);
+            add = rem; add.x = x; add.y = y;
+            has_add = true;
+        } break;
+        case 6: if (has_rem) {  // GaussianShapeTransformKernel.sample_perturbation :128-143
+            param_id = min(2, (int)(u01f(r0.w) * 3.0f));
+            double dummy;
+            box_muller(r1.x, r1.y, r1.z, r1.w, &d0, &dummy);
+            d0 *= c.k.trf_sigma[param_id];
+            R v = (param_id == 0 ? rem.size : (param_id == 1 ? rem.ratio : rem.angle)) + (R)d0;
+            const R vmax = (R)mark_vmax(param_id);
+            if (param_id == 2) v = v - r_floor(v / vmax) * vmax;  // python % on a cyclic mark
+            else v = r_min(r_max(v, (R)0), vmax);
+            if (param_id == 2 && !(v < vmax)) v = 0;
+            add = rem;
+            if (param_id == 0) add.size = v; else if (param_id == 1) add.ratio = v; else add.angle = v;
+            const int nc_ = value_to_class<R>(param_id, v);
+            add.cls = (rem.cls & ~(0xffu << (8 * param_id))) | ((uint32_t)nc_ << (8 * param_id));
+            fill_geometry(add);
+            has_add = true;
+        } break;
+        default: if (has_rem) {  // DataDrivenShapeTransformKernel.sample_perturbation :179-200
+            param_id = min(2, (int)(u01f(r0.w) * 3.0f));
+            new_class = sample_mark_class(c, param_id, rem.x, rem.y, u01f(r1.x), lane);
+            const R v = mark_edge<R>(param_id, new_class);
+            add = rem;
+            if (param_id == 0) add.size = v; else if (param_id == 1) add.ratio = v; else add.angle = v;
+            add.cls = (rem.cls & ~(0xffu << (8 * param_id))) | ((uint32_t)new_class << (8 * param_id));
+            fill_geometry(add);
+            has_add = true;
+        } break;
+        }
+        if (has_add && has_rem) {
+            if (kernel == 4 || kernel == 5) {
+                const bool stays = add.x >= x0 && add.x < x1 && add.y >= y0 && add.y < y1;
+                const bool short_move = abs(add.x - rem.x) <= 16 && abs(add.y - rem.y) <= 16;
+                if (in_cell_moves ? !stays : !short_move) valid = false;  // symmetric restriction -> plain rejection
+                if (valid) fill_unit_energies(c, add);
+            } else {
+                fill_unit_energies(c, add);  // classes changed
+            }
+        }
+        if (valid && has_add) {  // a full destination cell rejects the proposal (capacity MPP_CELL_CAPACITY)
+            const int dcell = cell_of(c, add.x, add.y);
+            uint32_t dm = __ldcg(c.mask + dcell);
+            if (has_rem && (rh >> 5) == (uint32_t)dcell) dm &= ~(1u << (rh & 31));
+            if (dm == 0xffffffffu) valid = false;
+        }
+        if (valid && (has_rem || has_add)) {
+            const R d = warp_delta(c, s, has_rem, rh, rem, has_add, add, lane);
+            double fwd, bwd;
+            proposal_probs(c, kernel, has_rem, rem, has_add, add, d0, d1, param_id, new_class, (double)nc, lambda, lane, &fwd, &bwd);
+            const double la = (-(double)d / temp) + log(bwd + MPP_EPS) - log(fwd + MPP_EPS);
+            const bool acc = log(u01(r2.z, r2.w) + MPP_EPS) < la;
+            if (acc) {
+                if (has_rem) erase_handle(c, rh, lane);
+                __syncwarp();
+                if (has_add) {
+                    if (lane == 0) add.uid = atomicAdd(c.next_uid, 1u);
+                    add.uid = __shfl_sync(MPP_FULL, add.uid, 0);
+                    insert_rec(c, add, lane);
+                }
+                __syncwarp();
+                ++n_acc;
+                if (has_add && !has_rem) { ++n_birth; ++dn; }
+                if (has_rem && !has_add) { ++n_death; --dn; }
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(c.counters + 0, (unsigned long long)per_visit);
+        atomicAdd(c.counters + 1, (unsigned long long)n_acc);
+        atomicAdd(c.counters + 2, (unsigned long long)n_birth);
+        atomicAdd(c.counters + 3, (unsigned long long)n_death);
+        if (dn) atomicAdd(c.n_objects, dn);
+    }
+}
+
+// ---- naive initial configuration (sample_rjmcmc.py:23-35) -------------------------------------------
+// Greedy distance NMS (utils/nms.py:68-109) == maximal independent set by priority: a pixel is kept iff no
+// kept pixel of higher priority lies within `thr`.  Solved in rounds: an undecided candidate that beats every
+// undecided candidate around it is kept, then everything around a kept pixel is suppressed.
+// state: 0 not a candidate, 1 undecided, 2 kept, 3 suppressed.  Priority = (score, flat index).
+__global__ void k_nms_threshold(const float *__restrict__ det, int n, float thr, unsigned char *__restrict__ state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) state[i] = det[i] >= thr ? 1 : 0;
+}
+__global__ void k_nms_select(const float *__restrict__ det, int H, int W, int rad, int rad2, unsigned char *state, int *changed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W || state[i] != 1) return;
+    const int x = i / W, y = i % W;
+    const float sc = det[i];
+    for (int dx = -rad; dx <= rad; ++dx)
+        for (int dy = -rad; dy <= rad; ++dy) {
+            if ((dx | dy) == 0 || dx * dx + dy * dy > rad2) continue;
+            const int px = x + dx, py = y + dy;
+            if (px < 0 || py < 0 || px >= H || py >= W) continue;
+            const int j = px * W + py;
+            const unsigned char st = state[j];
+            if (st == 2) return;  // will be suppressed by k_nms_suppress
+            if (st == 1) { const float o = det[j]; if (o > sc || (o == sc && j > i)) return; }
+        }
+    state[i] = 2;  // no undecided neighbour can ever beat it
+    *changed = 1;
+}
+__global__ void k_nms_suppress(int H, int W, int rad, int rad2, unsigned char *state, int *remaining) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W || state[i] != 1) return;
+    const int x = i / W, y = i % W;
+    for (int dx = -rad; dx <= rad; ++dx)
+        for (int dy = -rad; dy <= rad; ++dy) {
+            if (dx * dx + dy * dy > rad2) continue;
+            const int px = x + dx, py = y + dy;
+            if (px < 0 || py < 0 || px >= H || py >= W) continue;
+            if (state[px * W + py] == 2) { state[i] = 3; return; }
+        }
+    *remaining = 1;
+}
+template <typename R>
+__global__ void k_nms_insert(Ctx<R> c, const unsigned char *__restrict__ state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.H * c.W || state[i] != 2) return;
+    const int x = i / c.W, y = i % c.W;
+    int cl[3];
+    for (int k = 0; k < 3; ++k) {  // np.argmax over the raw mark rows (first maximum)
+        const float *row = mark_row(c, k, x, y);
+        int best = 0; float bv = row[0];
+        for (int b = 1; b < MPP_N_CLASSES; ++b) { const float v = row[b]; if (v > bv) { bv = v; best = b; } }
+        cl[k] = best;
+    }
+    const Rec<R> r = make_rec(c, x, y, mark_edge<R>(0, cl[0]), mark_edge<R>(1, cl[1]), mark_edge<R>(2, cl[2]),
+                              pack_cls(cl[0], cl[1], cl[2]), atomicAdd(c.next_uid, 1u));
+    const int cell = cell_of(c, x, y);
+    for (;;) {
+        const uint32_t msk = atomicOr(c.mask + cell, 0u);
+        if (msk == 0xffffffffu) { atomicOr(c.err, ERRF_CELL_FULL); return; }
+        const int slot = __ffs(~msk) - 1;
+        const uint32_t old = atomicOr(c.mask + cell, 1u << slot);
+        if (!(old & (1u << slot))) { store_rec(c.recs + (size_t)cell * 32 + slot, r); atomicAdd(c.n_objects, 1); return; }
+    }
+}
+
+// ---- multi-GPU halo: pack / unpack the objects of a band of rows -----------------------------------
+template <typename R>
+__global__ void k_pack_rows(Ctx<R> c, int row_lo, int row_hi, double *__restrict__ buf, int capacity, int *__restrict__ count) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c.ncell) return;
+    const int cx0 = (cell / c.ny) * 32;
+    if (cx0 + 32 <= row_lo || cx0 >= row_hi) return;
+    uint32_t msk = c.mask[cell];
+    while (msk) {
+        const int slot = __ffs(msk) - 1;
+        msk &= msk - 1;
+        const Rec<R> r = load_rec(c.recs + (size_t)cell * 32 + slot);
+        if (r.x < row_lo || r.x >= row_hi) continue;
+        const int pos = atomicAdd(count, 1);
+        if (pos < capacity) {
+            double *o = buf + (size_t)pos * 8;
+            o[0] = r.x; o[1] = r.y; o[2] = (double)r.size; o[3] = (double)r.ratio; o[4] = (double)r.angle;
+            o[5] = (double)r.cls; o[6] = (double)r.uid; o[7] = 0.0;
+        }
+    }
+}
+template <typename R>
+__global__ void k_erase_rows(Ctx<R> c, int row_lo, int row_hi) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c.ncell) return;
+    const int cx0 = (cell / c.ny) * 32;
+    if (cx0 + 32 <= row_lo || cx0 >= row_hi) return;
+    uint32_t msk = c.mask[cell], keep = msk;
+    int removed = 0;
+    while (msk) {
+        const int slot = __ffs(msk) - 1;
+        msk &= msk - 1;
+        const int x = c.recs[(size_t)cell * 32 + slot].x;
+        if (x >= row_lo && x < row_hi) { keep &= ~(1u << slot); ++removed; }
+    }
+    if (removed) { c.mask[cell] = keep; atomicSub(c.n_objects, removed); }
+}
+template <typename R>
+__global__ void k_unpack_rows(Ctx<R> c, const double *__restrict__ buf, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *o = buf + (size_t)i * 8;
+    const int x = (int)o[0], y = (int)o[1];
+    if (x < 0 || y < 0 || x >= c.H || y >= c.W) { atomicOr(c.err, ERRF_OUT_OF_BOUNDS); return; }
+    const Rec<R> r = make_rec(c, x, y, (R)o[2], (R)o[3], (R)o[4], (uint32_t)o[5], (uint32_t)o[6]);
+    const int cell = cell_of(c, x, y);
+    for (;;) {
+        const uint32_t msk = atomicOr(c.mask + cell, 0u);
+        if (msk == 0xffffffffu) { atomicOr(c.err, ERRF_CELL_FULL); return; }
+        const int slot = __ffs(~msk) - 1;
+        const uint32_t old = atomicOr(c.mask + cell, 1u << slot);
+        if (!(old & (1u << slot))) { store_rec(c.recs + (size_t)cell * 32 + slot, r); atomicAdd(c.n_objects, 1); return; }
+    }
+}
+
+// ================================================================================================ C ABI
+static const int WARPS_PER_BLOCK = 4;
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" {
+
+int mpp_abi_version(void) { return MPP_ABI_VERSION; }
+const char *mpp_last_error(void) { return g_last_error.c_str(); }
+int mpp_abi_struct_size(int which) {
+    switch (which) {
+    case 0: return (int)sizeof(mpp_model_params);
+    case 1: return (int)sizeof(mpp_kernel_params);
+    case 2: return (int)sizeof(mpp_proposal);
+    case 3: return (int)sizeof(mpp_step_result);
+    default: return -1;
+    }
+}
+
+int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precision, void *stream) {
+    if (!out || height <= 0 || width <= 0) return fail(MPP_ERR_INVALID, "mpp_ctx_create: bad arguments");
+    if (precision != MPP_PRECISION_FP32 && precision != MPP_PRECISION_FP64) return fail(MPP_ERR_INVALID, "mpp_ctx_create: precision");
+    CUDA_TRY(cudaSetDevice(device));
+    mpp_ctx *h = new (std::nothrow) mpp_ctx();
+    if (!h) return fail(MPP_ERR_INVALID, "out of host memory");
+    h->device = device; h->stream = (cudaStream_t)stream; h->precision = precision;
+    h->H = height; h->W = width;
+    h->nx = (height + MPP_CELL_SIZE - 1) / MPP_CELL_SIZE;  // point_set.py:60-61
+    h->ny = (width + MPP_CELL_SIZE - 1) / MPP_CELL_SIZE;
+    h->ncell = h->nx * h->ny;
+    const size_t rec = precision == MPP_PRECISION_FP64 ? sizeof(Rec<double>) : sizeof(Rec<float>);
+    CUDA_TRY(cudaMalloc(&h->d_mask, sizeof(uint32_t) * h->ncell));
+    CUDA_TRY(cudaMalloc(&h->d_recs, rec * (size_t)h->ncell * MPP_CELL_CAPACITY));
+    CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * h->ncell));
+    CUDA_TRY(cudaMalloc(&h->d_scan, sizeof(int) * (h->ncell + 1)));
+    CUDA_TRY(cudaMalloc(&h->d_nobj, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_next_uid, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 4));
+    CUDA_TRY(cudaMallocHost(&h->h_pinned, 128));
+    CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_recs, 0, rec * (size_t)h->ncell * MPP_CELL_CAPACITY, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_next_uid, 0, sizeof(uint32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    memset(&h->m, 0, sizeof(h->m));
+    memset(&h->k, 0, sizeof(h->k));
+    // dynamic shared memory opt-in for the warp-scratch kernels
+    CUDA_TRY(set_smem(k_energy_vectors<float>, WARPS_PER_BLOCK * sizeof(Scratch<float>)));
+    CUDA_TRY(set_smem(k_energy_vectors<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
+    CUDA_TRY(set_smem(k_delta_batch<float>, WARPS_PER_BLOCK * sizeof(Scratch<float>)));
+    CUDA_TRY(set_smem(k_delta_batch<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
+    CUDA_TRY(set_smem(k_sweep<float>, WARPS_PER_BLOCK * sizeof(Scratch<float>)));
+    CUDA_TRY(set_smem(k_sweep<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
+    CUDA_TRY(set_smem(k_replay<float>, sizeof(Scratch<float>)));
+    CUDA_TRY(set_smem(k_replay<double>, sizeof(Scratch<double>)));
+    *out = h;
+    return MPP_OK;
+}
+
+int mpp_ctx_destroy(mpp_ctx *h) {
+    if (!h) return MPP_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_scan); cudaFree(h->d_nobj);
+    cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
+    cudaFreeHost(h->h_pinned);
+    delete h;
+    return MPP_OK;
+}
+
+int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_sum) {
+    if (!h || !det || !marks) return fail(MPP_ERR_INVALID, "mpp_set_maps: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->det = det; h->marks = marks;
+    const int blocks = (h->ncell + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    k_cell_mass<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->ny, h->ncell, h->d_cell_cdf);
+    k_scan_double<<<1, 1024, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
+    CUDA_TRY(cudaGetLastError());
+    if (det_sum > 0.0) {
+        h->det_sum = (float)det_sum;
+    } else {
+        double *tmp = reinterpret_cast<double *>(h->h_pinned);
+        CUDA_TRY(cudaMemcpyAsync(tmp, h->d_cell_cdf + (h->ncell - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->det_sum = (float)*tmp;
+    }
+    h->maps_set = true;
+    return MPP_OK;
+}
+
+int mpp_set_model(mpp_ctx *h, const mpp_model_params *p) {
+    if (!h || !p) return fail(MPP_ERR_INVALID, "mpp_set_model: null argument");
+    if (p->setup != MPP_SETUP_LEGACY && p->setup != MPP_SETUP_NO_CALIBRATION) return fail(MPP_ERR_INVALID, "mpp_set_model: setup");
+    if (p->combinator < 0 || p->combinator > MPP_COMB_MANUAL_HIERARCHICAL) return fail(MPP_ERR_INVALID, "mpp_set_model: combinator");
+    if (p->combinator == MPP_COMB_HIERARCHICAL && p->setup != MPP_SETUP_LEGACY)
+        return fail(MPP_ERR_INVALID, "hierarchical combinator needs the legacy term names (hierarchical.py:22-29)");
+    if (p->overlap_max_dist > MPP_CELL_SIZE || p->align_max_dist > MPP_CELL_SIZE)
+        return fail(MPP_ERR_INVALID, "interaction distances above the 32-px cell size are not supported");
+    ModelDev &m = h->m;
+    m.setup = p->setup; m.comb = p->combinator; m.ratio_prior = p->ratio_prior; m.rewarding = p->rewarding;
+    m.n_terms = p->setup == MPP_SETUP_LEGACY ? 5 : (p->ratio_prior ? 8 : 7);
+    m.ov_d2 = (int)floor(p->overlap_max_dist * p->overlap_max_dist);
+    m.al_d2 = (int)floor(p->align_max_dist * p->align_max_dist);
+    m.max_d2 = m.ov_d2 > m.al_d2 ? m.ov_d2 : m.al_d2;
+    m.pos_thr = (float)p->pos_threshold;
+    for (int i = 0; i < 3; ++i) { m.coef[i] = (float)p->remap_coef[i]; m.icpt[i] = (float)p->remap_intercept[i]; }
+    m.min_area = p->min_area; m.max_area = p->max_area; m.target_ratio = p->target_ratio;
+    for (int i = 0; i < MPP_MAX_TERMS; ++i) m.w[i] = p->comb_w[i];
+    m.bias = p->comb_bias; m.thr = p->comb_threshold;
+    h->model_set = true;
+    return MPP_OK;
+}
+
+int mpp_set_kernels(mpp_ctx *h, const mpp_kernel_params *p) {
+    if (!h || !p) return fail(MPP_ERR_INVALID, "mpp_set_kernels: null argument");
+    if (!(p->intensity > 0.0)) return fail(MPP_ERR_INVALID, "mpp_set_kernels: intensity must be > 0");
+    if (p->data_translation_max_delta < 0 || p->data_translation_max_delta > 15) return fail(MPP_ERR_INVALID, "mpp_set_kernels: max_delta in [0,15]");
+    KernDev &k = h->k;
+    for (int i = 0; i < 8; ++i) k.p[i] = p->p_kernel[i];
+    k.intensity = p->intensity;
+    k.trl_sigma = p->gauss_translation_sigma;
+    k.trl_max_delta = p->data_translation_max_delta;
+    const double range[3] = {32.0, 1.0, 3.14159265358979323846};  // transform_kernels.py:122
+    for (int i = 0; i < 3; ++i) k.trf_sigma[i] = p->gauss_transform_sigma * range[i];
+    h->kernels_set = true;
+    return MPP_OK;
+}
+
+#define NEED(h, cond, what) do { if (!(h)) return fail(MPP_ERR_INVALID, "null ctx"); if (!(cond)) return fail(MPP_ERR_STATE, what); } while (0)
+
+int mpp_add_objects(mpp_ctx *h, const int32_t *xy, const double *marks, const uint32_t *cls, const uint32_t *uid, int n,
+                    uint32_t *out_handle) {
+    NEED(h, h->maps_set && h->model_set, "mpp_add_objects: set maps and model first");
+    if (n < 0 || (n > 0 && (!xy || !marks))) return fail(MPP_ERR_INVALID, "mpp_add_objects: bad arguments");
+    if (n == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    DISPATCH(h, (k_add_objects<R><<<(n + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), xy, marks, cls, uid, n, out_handle)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
+int mpp_remove_objects(mpp_ctx *h, const uint32_t *handle, int n) {
+    NEED(h, true, "");
+    if (n < 0 || (n > 0 && !handle)) return fail(MPP_ERR_INVALID, "mpp_remove_objects: bad arguments");
+    if (n == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    DISPATCH(h, (k_remove_objects<R><<<(n + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), handle, n)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
+int mpp_clear_objects(mpp_ctx *h) {
+    NEED(h, true, "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
+    return MPP_OK;
+}
+
+int mpp_num_objects(mpp_ctx *h, int *n_host) {
+    NEED(h, n_host != nullptr, "mpp_num_objects: null output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->h_pinned, h->d_nobj, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *n_host = *h->h_pinned;
+    return MPP_OK;
+}
+
+int mpp_read_objects(mpp_ctx *h, int capacity, uint32_t *handle, int32_t *xy, double *marks, uint32_t *uid, int *n_host) {
+    NEED(h, true, "");
+    if (capacity < 0) return fail(MPP_ERR_INVALID, "mpp_read_objects: capacity");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_scan_population<<<1, 1024, 0, h->stream>>>(h->d_mask, h->ncell, h->d_scan);
+    if (capacity > 0)
+        DISPATCH(h, (k_read_objects<R><<<(h->ncell + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), h->d_scan, capacity, handle, xy, marks, uid)));
+    CUDA_TRY(cudaGetLastError());
+    if (n_host) {
+        CUDA_TRY(cudaMemcpyAsync(h->h_pinned, h->d_scan + h->ncell, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        *n_host = *h->h_pinned;
+    }
+    return MPP_OK;
+}
+
+int mpp_energy_vectors(mpp_ctx *h, const uint32_t *handle, int n, double *out_vectors, double *out_combined, double *out_totals) {
+    NEED(h, h->maps_set && h->model_set, "mpp_energy_vectors: set maps and model first");
+    if (n < 0 || (n > 0 && !handle)) return fail(MPP_ERR_INVALID, "mpp_energy_vectors: bad arguments");
+    if (out_totals && n > 0 && (!out_vectors || !out_combined)) return fail(MPP_ERR_INVALID, "mpp_energy_vectors: totals need both outputs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n > 0) {
+        const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        DISPATCH(h, (k_energy_vectors<R><<<blocks, WARPS_PER_BLOCK * 32, WARPS_PER_BLOCK * sizeof(Scratch<R>), h->stream>>>(
+                        device_view<R>(h), handle, n, out_vectors, out_combined)));
+    }
+    if (out_totals) k_totals<<<1, 256, 0, h->stream>>>(out_vectors, out_combined, n, out_totals);
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+int mpp_delta_batch(mpp_ctx *h, const mpp_proposal *props, int m, double *out_delta) {
+    NEED(h, h->maps_set && h->model_set, "mpp_delta_batch: set maps and model first");
+    if (m < 0 || (m > 0 && (!props || !out_delta))) return fail(MPP_ERR_INVALID, "mpp_delta_batch: bad arguments");
+    if (m == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    DISPATCH(h, (k_delta_batch<R><<<blocks, WARPS_PER_BLOCK * 32, WARPS_PER_BLOCK * sizeof(Scratch<R>), h->stream>>>(
+                    device_view<R>(h), props, m, out_delta)));
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+int mpp_replay(mpp_ctx *h, const mpp_proposal *props, int m, double t0, double alpha_t, double t_target, mpp_step_result *out) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_replay: set maps, model and kernels first");
+    if (m < 0 || (m > 0 && (!props || !out)) || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_replay: bad arguments");
+    if (m == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    DISPATCH(h, (k_replay<R><<<1, 32, sizeof(Scratch<R>), h->stream>>>(device_view<R>(h), props, m, t0, alpha_t, t_target, out)));
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+int mpp_run_sweeps(mpp_ctx *h, int n_sweeps, int per_visit, int stride, double t0, double alpha_t, double t_target,
+                   uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_sweeps: set maps, model and kernels first");
+    if (n_sweeps < 0 || per_visit < 1 || stride < 3 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_sweeps: bad arguments (stride >= 3)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double temp = t0;
+    for (int s = 0; s < n_sweeps; ++s) {
+        for (int ci = 0; ci < stride; ++ci)
+            for (int cj = 0; cj < stride; ++cj) {
+                const int n_ai = ci < h->nx ? (h->nx - ci + stride - 1) / stride : 0;
+                const int n_aj = cj < h->ny ? (h->ny - cj + stride - 1) / stride : 0;
+                const int n_active = n_ai * n_aj;
+                if (n_active == 0) continue;
+                const int blocks = (n_active + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+                DISPATCH(h, (k_sweep<R><<<blocks, WARPS_PER_BLOCK * 32, WARPS_PER_BLOCK * sizeof(Scratch<R>), h->stream>>>(
+                                device_view<R>(h), stride, ci, cj, n_ai, n_aj, per_visit, temp, seed, sweep_offset + (uint64_t)s)));
+            }
+        if (temp > t_target) temp *= alpha_t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (counters_host) {
+        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(h->h_pinned);
+        CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 4; ++i) counters_host[i] = tmp[i];
+        return check_device_errors(h);
+    }
+    return MPP_OK;
+}
+
+int mpp_sample_births(mpp_ctx *h, int n, uint64_t seed, int32_t *out) {
+    NEED(h, h->maps_set, "mpp_sample_births: set maps first");
+    if (n < 0 || (n > 0 && !out)) return fail(MPP_ERR_INVALID, "mpp_sample_births: bad arguments");
+    if (n == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    DISPATCH(h, (k_sample_births<R><<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(device_view<R>(h), n, seed, out)));
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+int mpp_naive_init(mpp_ctx *h, double detection_threshold, double nms_distance, int *n_host) {
+    NEED(h, h->maps_set && h->model_set, "mpp_naive_init: set maps and model first");
+    if (nms_distance < 0 || nms_distance > 32) return fail(MPP_ERR_INVALID, "mpp_naive_init: nms_distance in [0,32]");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = h->H * h->W;
+    if (!h->d_nms_state) CUDA_TRY(cudaMalloc(&h->d_nms_state, (size_t)n));
+    const int rad = (int)floor(nms_distance), rad2 = (int)floor(nms_distance * nms_distance);
+    const int blocks = (n + 255) / 256;
+    int *flags = reinterpret_cast<int *>(h->d_counters);  // reuse: 2 ints
+    k_nms_threshold<<<blocks, 256, 0, h->stream>>>(h->det, n, (float)detection_threshold, h->d_nms_state);
+    for (int round = 0; round < 4096; ++round) {
+        CUDA_TRY(cudaMemsetAsync(flags, 0, 2 * sizeof(int), h->stream));
+        k_nms_select<<<blocks, 256, 0, h->stream>>>(h->det, h->H, h->W, rad, rad2, h->d_nms_state, flags);
+        k_nms_suppress<<<blocks, 256, 0, h->stream>>>(h->H, h->W, rad, rad2, h->d_nms_state, flags + 1);
+        CUDA_TRY(cudaMemcpyAsync(h->h_pinned, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!h->h_pinned[1]) break;
+        if (!h->h_pinned[0]) return fail(MPP_ERR_CUDA, "mpp_naive_init: NMS did not progress");
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    DISPATCH(h, (k_nms_insert<R><<<blocks, 256, 0, h->stream>>>(device_view<R>(h), h->d_nms_state)));
+    CUDA_TRY(cudaGetLastError());
+    int rc = check_device_errors(h);
+    if (rc != MPP_OK) return rc;
+    if (n_host) return mpp_num_objects(h, n_host);
+    return MPP_OK;
+}
+
+int mpp_pack_rows(mpp_ctx *h, int row_lo, int row_hi, double *buf, int capacity, int *n_host) {
+    NEED(h, true, "");
+    if (capacity < 0 || (capacity > 0 && !buf) || !n_host) return fail(MPP_ERR_INVALID, "mpp_pack_rows: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int *count = h->d_scan;  // scratch
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), h->stream));
+    DISPATCH(h, (k_pack_rows<R><<<(h->ncell + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), row_lo, row_hi, buf, capacity, count)));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->h_pinned, count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *n_host = *h->h_pinned;
+    if (*n_host > capacity) return fail(MPP_ERR_INVALID, "mpp_pack_rows: buffer too small");
+    return MPP_OK;
+}
+
+int mpp_unpack_rows(mpp_ctx *h, int row_lo, int row_hi, const double *buf, int n) {
+    NEED(h, h->maps_set && h->model_set, "mpp_unpack_rows: set maps and model first");
+    if (n < 0 || (n > 0 && !buf)) return fail(MPP_ERR_INVALID, "mpp_unpack_rows: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    DISPATCH(h, (k_erase_rows<R><<<(h->ncell + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), row_lo, row_hi)));
+    if (n > 0) DISPATCH(h, (k_unpack_rows<R><<<(n + 127) / 128, 128, 0, h->stream>>>(device_view<R>(h), buf, n)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
+}  // extern "C"

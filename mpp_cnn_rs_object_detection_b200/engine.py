@@ -1,0 +1,293 @@
+"""Thin Python owner of one device context (one scene / one chain).  PyTorch is used only for device memory and
+streams; every computation is a call into libmpp_b200.so through the C ABI of include/mpp_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LEGACY_NAMES = ["PositionEnergy", "ShapeEnergy", "RectangleOverlapEnergy", "ShapeAlignmentEnergy", "AreaPriorEnergy"]
+NOCALIB_NAMES = ["PositionEnergy", "SizeEnergy", "RatioEnergy", "AngleEnergy", "OverlapPriorEnergy", "AlignmentPriorEnergy",
+                 "AreaPriorEnergy", "RatioPriorEnergy"]
+
+
+def kernel_probabilities(use_split_merge: bool = False) -> np.ndarray:
+    """Kernel choice probabilities of make_kernels (rjmcmc_sampler/kernels/make_kernels.py:13-24,76-86,163-166)."""
+    if use_split_merge:
+        raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
+
+    def normalize(a):
+        a = np.array(a, dtype=np.float64)
+        return a / np.linalg.norm(a, ord=1)
+
+    p_bd, p_trl, p_trf = normalize([1, 1, 1])
+    p_bd_unif, p_bd_data = normalize([1, 2])
+    p_trl_gaus, p_trl_data = normalize([1, 2])
+    p_trf_gaus, p_trf_data = normalize([1, 2])
+    p = np.array([0.5 * p_bd_unif * p_bd, 0.5 * p_bd_unif * p_bd, 0.5 * p_bd_data * p_bd, 0.5 * p_bd_data * p_bd,
+                  p_trl * p_trl_gaus, p_trl * p_trl_data, p_trf * p_trf_gaus, p_trf * p_trf_data])
+    if abs(1 - np.sum(p)) < 1e-8:
+        p = p / np.sum(p)
+    return p
+
+
+@dataclass
+class ModelSpec:
+    """Host description of the energy model (terms + combinator) sent to mpp_set_model."""
+    setup: str = "legacy"  # 'legacy' | 'nocalib'
+    pos_threshold: float = 0.0
+    remap_coefs: Sequence[float] = (1.0, 1.0, 1.0)
+    remap_intercepts: Sequence[float] = (0.0, 0.0, 0.0)
+    min_area: float = 0.0
+    max_area: float = 1e9
+    ratio_prior: bool = False
+    target_ratio: float = 0.5
+    rewarding: bool = True
+    overlap_max_dist: float = 32.0
+    align_max_dist: float = 16.0
+    combinator: str = "raw"  # 'raw' | 'hierarchical' | 'logistic' | 'manual'
+    comb_w: Sequence[float] = field(default_factory=lambda: [0.0] * 8)
+    comb_bias: float = 0.0
+    comb_threshold: float = 0.0
+
+    @property
+    def names(self):
+        if self.setup == "legacy":
+            return list(LEGACY_NAMES)
+        return list(NOCALIB_NAMES if self.ratio_prior else NOCALIB_NAMES[:7])
+
+    def to_c(self) -> _lib.ModelParams:
+        p = _lib.ModelParams()
+        p.setup = {"legacy": _lib.SETUP_LEGACY, "nocalib": _lib.SETUP_NO_CALIBRATION}[self.setup]
+        p.combinator = {"raw": _lib.COMB_RAW_SUM, "hierarchical": _lib.COMB_HIERARCHICAL, "logistic": _lib.COMB_LOGISTIC,
+                        "manual": _lib.COMB_MANUAL_HIERARCHICAL}[self.combinator]
+        p.ratio_prior = int(self.ratio_prior)
+        p.rewarding = int(self.rewarding)
+        p.pos_threshold = float(self.pos_threshold)
+        for i in range(3):
+            p.remap_coef[i] = float(self.remap_coefs[i])
+            p.remap_intercept[i] = float(self.remap_intercepts[i])
+        p.min_area, p.max_area, p.target_ratio = float(self.min_area), float(self.max_area), float(self.target_ratio)
+        p.overlap_max_dist, p.align_max_dist = float(self.overlap_max_dist), float(self.align_max_dist)
+        w = list(self.comb_w) + [0.0] * 8
+        for i in range(8):
+            p.comb_w[i] = float(w[i])
+        p.comb_bias, p.comb_threshold = float(self.comb_bias), float(self.comb_threshold)
+        return p
+
+
+def pack_classes(classes: np.ndarray) -> np.ndarray:
+    c = np.asarray(classes, dtype=np.uint32).reshape(-1, 3)
+    return (c[:, 0] | (c[:, 1] << 8) | (c[:, 2] << 16)).astype(np.uint32)
+
+
+_EDGES = [np.linspace(0.0, v, 33)[:-1] for v in (32.0, 1.0, math.pi)]  # models/shape_net/mappings.py:17
+
+
+def classes_of_marks(marks: np.ndarray) -> np.ndarray:
+    """ValueMapping.value_to_class in float64 on the host (mappings.py:45-61): max{c : v >= edge_c}."""
+    m = np.asarray(marks, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(m.shape, dtype=np.int64)
+    for i in range(3):
+        c = np.searchsorted(_EDGES[i], m[:, i], side="right") - 1
+        if np.any(c < 0):
+            raise ValueError(f"mark {i} below its mapping's v_min")
+        out[:, i] = np.minimum(c, 31)
+    return out
+
+
+class Engine:
+    """One mpp_ctx.  Not thread-safe; bound to one CUDA device and the current torch stream at creation."""
+
+    def __init__(self, shape: Tuple[int, int], device: Optional[torch.device] = None, precision: str = "fp32"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mpp_cnn_rs_object_detection_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.precision = precision
+        self.stream = torch.cuda.current_stream(self.device)
+        ctx = C.c_void_p()
+        _lib.check(self.lib.mpp_ctx_create(C.byref(ctx), self.device.index, self.shape[0], self.shape[1],
+                                           _lib.PRECISION_FP64 if precision == "fp64" else _lib.PRECISION_FP32,
+                                           C.c_void_p(self.stream.cuda_stream)))
+        self.ctx = ctx
+        self.model: Optional[ModelSpec] = None
+        self._det = None
+        self._marks = None
+        self.launches = 0  # kernels launched through this engine (bench gpu_launches)
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.lib.mpp_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ setup
+    def _dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def set_maps(self, det, marks, det_sum: Optional[float] = None):
+        """det (H,W) f32; marks (3,H,W,32) f32 or a list of three (H,W,32).  Tensors already on the device are used
+        in place (no copy).  det_sum: float(np.sum(det)) as numpy computes it, for bit-parity of the densities."""
+        if isinstance(marks, (list, tuple)):
+            if isinstance(marks[0], torch.Tensor):
+                marks = torch.stack([m.to(self.device) for m in marks])
+            else:
+                marks = np.stack([np.asarray(m, dtype=np.float32) for m in marks])
+        if det_sum is None and not isinstance(det, torch.Tensor):
+            det_sum = float(np.sum(np.asarray(det, dtype=np.float32)))
+        self._det = self._dev(det, torch.float32)
+        self._marks = self._dev(marks, torch.float32)
+        assert tuple(self._det.shape) == self.shape, "detection map shape"
+        assert tuple(self._marks.shape) == (3,) + self.shape + (32,), "mark maps shape"
+        _lib.check(self.lib.mpp_set_maps(self.ctx, self._det.data_ptr(), self._marks.data_ptr(),
+                                         float(det_sum) if det_sum is not None else -1.0))
+        self.launches += 2
+
+    def set_model(self, model: ModelSpec):
+        self.model = model
+        p = model.to_c()
+        _lib.check(self.lib.mpp_set_model(self.ctx, C.byref(p)))
+
+    def set_kernels(self, intensity: float, p_kernel: Optional[np.ndarray] = None, translation_sigma: float = 2.0,
+                    max_delta: int = 8, transform_sigma: float = 0.1):
+        p = _lib.KernelParams()
+        pk = kernel_probabilities() if p_kernel is None else np.asarray(p_kernel, dtype=np.float64)
+        for i in range(8):
+            p.p_kernel[i] = float(pk[i])
+        p.intensity = float(intensity)
+        p.gauss_translation_sigma = float(translation_sigma)
+        p.data_translation_max_delta = int(max_delta)
+        p.gauss_transform_sigma = float(transform_sigma)
+        _lib.check(self.lib.mpp_set_kernels(self.ctx, C.byref(p)))
+
+    # ------------------------------------------------------------------------------------------ objects
+    def add_objects(self, xy, marks, classes=None, uid=None) -> np.ndarray:
+        xy = np.ascontiguousarray(np.asarray(xy, dtype=np.int32).reshape(-1, 2))
+        marks = np.ascontiguousarray(np.asarray(marks, dtype=np.float64).reshape(-1, 3))
+        n = len(xy)
+        if n == 0:
+            return np.zeros((0,), dtype=np.uint32)
+        if classes is None:
+            classes = classes_of_marks(marks)
+        d_xy, d_m = self._dev(xy, torch.int32), self._dev(marks, torch.float64)
+        d_c = self._dev(pack_classes(classes).astype(np.int64), torch.int64).to(torch.int32)  # bit pattern of u32
+        d_u = None if uid is None else self._dev(np.asarray(uid, dtype=np.int64), torch.int64).to(torch.int32)
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mpp_add_objects(self.ctx, d_xy.data_ptr(), d_m.data_ptr(), d_c.data_ptr(),
+                                            None if d_u is None else d_u.data_ptr(), n, out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy().view(np.uint32)
+
+    def remove_objects(self, handles):
+        h = np.ascontiguousarray(np.asarray(handles, dtype=np.uint32).reshape(-1))
+        if len(h) == 0:
+            return
+        d = self._dev(h.view(np.int32), torch.int32)
+        _lib.check(self.lib.mpp_remove_objects(self.ctx, d.data_ptr(), len(h)))
+        self.launches += 1
+
+    def clear(self):
+        _lib.check(self.lib.mpp_clear_objects(self.ctx))
+
+    def __len__(self):
+        n = C.c_int()
+        _lib.check(self.lib.mpp_num_objects(self.ctx, C.byref(n)))
+        return n.value
+
+    def read_objects(self):
+        """(handles u32 [N], xy i32 [N,2], marks f64 [N,3], uid u32 [N]) in cell-major order."""
+        n = len(self)
+        cap = max(n, 1)
+        h = torch.empty(cap, dtype=torch.int32, device=self.device)
+        xy = torch.empty((cap, 2), dtype=torch.int32, device=self.device)
+        m = torch.empty((cap, 3), dtype=torch.float64, device=self.device)
+        u = torch.empty(cap, dtype=torch.int32, device=self.device)
+        cnt = C.c_int()
+        _lib.check(self.lib.mpp_read_objects(self.ctx, cap, h.data_ptr(), xy.data_ptr(), m.data_ptr(), u.data_ptr(), C.byref(cnt)))
+        self.launches += 2
+        n = min(cnt.value, cap)
+        return (h[:n].cpu().numpy().view(np.uint32), xy[:n].cpu().numpy(), m[:n].cpu().numpy(), u[:n].cpu().numpy().view(np.uint32))
+
+    # ------------------------------------------------------------------------------------------ energies
+    def energy_vectors(self, handles):
+        """(vectors f64 [N,T], combined f64 [N], raw_total, combined_total) for the objects named by `handles`."""
+        h = np.ascontiguousarray(np.asarray(handles, dtype=np.uint32).reshape(-1))
+        n = len(h)
+        t = len(self.model.names)
+        if n == 0:
+            return np.zeros((0, t)), np.zeros((0,)), 0.0, 0.0
+        d = self._dev(h.view(np.int32), torch.int32)
+        vec = torch.empty((n, _lib.MAX_TERMS), dtype=torch.float64, device=self.device)
+        comb = torch.empty(n, dtype=torch.float64, device=self.device)
+        tot = torch.empty(2, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mpp_energy_vectors(self.ctx, d.data_ptr(), n, vec.data_ptr(), comb.data_ptr(), tot.data_ptr()))
+        self.launches += 2
+        tot = tot.cpu().numpy()
+        return vec.cpu().numpy()[:, :t], comb.cpu().numpy(), float(tot[0]), float(tot[1])
+
+    def delta_batch(self, proposals: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(proposals, dtype=_lib.PROPOSAL_DTYPE)
+        m = len(p)
+        if m == 0:
+            return np.zeros((0,))
+        d = torch.as_tensor(p.view(np.uint8).reshape(m, -1)).to(self.device)
+        out = torch.empty(m, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mpp_delta_batch(self.ctx, d.data_ptr(), m, out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy()
+
+    def replay(self, proposals: np.ndarray, t0: float, alpha_t: float, t_target: float = 0.0) -> np.ndarray:
+        p = np.ascontiguousarray(proposals, dtype=_lib.PROPOSAL_DTYPE)
+        m = len(p)
+        d = torch.as_tensor(p.view(np.uint8).reshape(m, -1)).to(self.device)
+        out = torch.zeros((m, _lib.STEP_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mpp_replay(self.ctx, d.data_ptr(), m, float(t0), float(alpha_t), float(t_target), out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy().view(_lib.STEP_RESULT_DTYPE).reshape(m)
+
+    def run_sweeps(self, n_sweeps: int, proposals_per_visit: int = 8, stride: int = 4, t0: float = 1.0, alpha_t: float = 1.0,
+                   t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True):
+        cnt = (C.c_ulonglong * 4)()
+        _lib.check(self.lib.mpp_run_sweeps(self.ctx, int(n_sweeps), int(proposals_per_visit), int(stride), float(t0),
+                                           float(alpha_t), float(t_target), int(seed), int(sweep_offset),
+                                           cnt if read_counters else None))
+        self.launches += int(n_sweeps) * stride * stride
+        return [int(v) for v in cnt] if read_counters else None
+
+    def sample_births(self, n: int, seed: int = 0) -> np.ndarray:
+        out = torch.empty((n, 5), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mpp_sample_births(self.ctx, int(n), int(seed), out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy()
+
+    def naive_init(self, detection_threshold: float, nms_distance: float = 6.0) -> int:
+        n = C.c_int()
+        _lib.check(self.lib.mpp_naive_init(self.ctx, float(detection_threshold), float(nms_distance), C.byref(n)))
+        return n.value
+
+    def pack_rows(self, row_lo: int, row_hi: int, capacity: int = 65536) -> torch.Tensor:
+        buf = torch.empty((capacity, 8), dtype=torch.float64, device=self.device)
+        n = C.c_int()
+        _lib.check(self.lib.mpp_pack_rows(self.ctx, int(row_lo), int(row_hi), buf.data_ptr(), capacity, C.byref(n)))
+        return buf[:n.value]
+
+    def unpack_rows(self, row_lo: int, row_hi: int, records: torch.Tensor):
+        rec = records.to(device=self.device, dtype=torch.float64).contiguous()
+        _lib.check(self.lib.mpp_unpack_rows(self.ctx, int(row_lo), int(row_hi), rec.data_ptr() if len(rec) else None, len(rec)))
