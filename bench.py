@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the MPP RJMCMC hot path (BASELINE.json metric: RJMCMC proposals/s and ms/image per B200).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU sampler on the host cores
+
+Workload (configs[2] of BASELINE.json): synthetic 2048x2048 DOTA-vehicle-like scene, ~2k oriented rectangles, hrcM
+energy model (legacy setup + hierarchical combinator with the shipped weights / calibration).  One *step* = one image's
+worth of sampling: `--sweeps` parallel colour sweeps, every 32-px cell performing `--per-visit` local proposals per
+sweep (defaults give 2.46 M proposals, the reference's own budget for a 2048^2 image: 81 patches x 30 257 steps).
+N > 1: every rank samples its own scene (independent images -> weak scaling, no data-path collective).
+
+`value`     : proposals/s with the maps already resident in HBM (CUDA events around K steps, max over ranks).
+`e2e`       : the same metric through the host-facing call: pinned host maps -> H2D -> cell masses -> initial
+              configuration -> sweeps -> D2H of the final configuration, all inside the timed region.
+`roofline`  : algorithmic bytes/proposal (recomputed with the run's K2 and acceptance) x proposals
+              per k_sweep launch / mean launch duration, against the measured HBM peak of MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle's sequential sampler on the host cores, reference decomposition (256^2 patches, one process
+              per core), bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rjmcmc_proposals_per_sec"
+UNIT = "proposals/s"
+
+# models_storage/mpp/mpp_hrcM/calibration.json + energy_combination_model.pkl (decoded)
+CALIB_HRCM = dict(detection_threshold=0.6464646464646465,
+                  coefs=(40.61517366849468, 37.691647645515616, 35.287160617991965),
+                  intercepts=(-3.4763386136080006, -2.389875684851162, -3.8677248427633804),
+                  min_area=23.553573615517713, max_area=166.58205129586045)
+HRC = dict(weights_data=(0.8, 0.2), weights_prior=(0.7058823529411764, 0.058823529411764705, 0.23529411764705882),
+           data_prior_weights=(0.5, 0.5), detection_threshold=0.0, bias=0.0)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--n-rect", type=int, default=0, help="candidate rectangles (0: 2600 per 2048^2, scaled by area)")
+    ap.add_argument("--sweeps", type=int, default=75)
+    ap.add_argument("--per-visit", type=int, default=8)
+    ap.add_argument("--stride", type=int, default=3)
+    ap.add_argument("--temperature", type=float, default=0.02)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-steps", type=int, default=4000, help="proposals per CPU worker in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def n_rect_for(args):
+    return args.n_rect or int(round(2600 * (args.size * args.size) / (2048.0 * 2048.0)))
+
+
+def workload_name(args):
+    return (f"synthetic {args.size}x{args.size} scene, {n_rect_for(args)} candidate rectangles (make_synth recipe), "
+            f"hrcM energies, fixed T={args.temperature}")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ roofline
+def bytes_per_proposal(k2: float, acceptance: float, h: int, w: int, p_kernel, window: int = 17) -> float:
+    """B = 8*C + 20*(1+K2) + 16*p_add + 16*p_dataBD + 8*ceil(log2 H + log2 W)*p_dataBirth
+    + 2*4*w^2*p_dataTrl + 128*p_dataTrf + 20*a   (C = 25 cells of the 5x5 block, K2 = mean objects in it)."""
+    p = np.asarray(p_kernel, dtype=np.float64)
+    p_add = 1.0 - (p[1] + p[3])
+    p_data_bd = p[2] + p[3]
+    return (8.0 * 25 + 20.0 * (1 + k2) + 16.0 * p_add + 16.0 * p_data_bd + 8.0 * math.ceil(math.log2(h) + math.log2(w)) * p[2]
+            + 2 * 4.0 * window * window * p[5] + 128.0 * p[7] + 20.0 * acceptance)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_patches(args, device):
+    from mpp_cnn_rs_object_detection_b200 import synth
+    from oracle import cpu_baseline as cb
+    objs, det, marks = synth.make_scene_torch(args.seed, (args.size, args.size), n_rect_for(args), device)
+    workers = cb.host_cores()
+    # crop on the device, move only the needed patches to the host
+    det_np = None
+    patches = []
+    h = w = args.size
+    for i in range(0, h, cb.PATCH):
+        for j in range(0, w, cb.PATCH):
+            if len(patches) >= workers:
+                break
+            i1, j1 = min(h, i + cb.PATCH), min(w, j + cb.PATCH)
+            sel = (objs[:, 0] >= i) & (objs[:, 0] < i1) & (objs[:, 1] >= j) & (objs[:, 1] < j1)
+            o = objs[sel].copy()
+            o[:, 0] -= i
+            o[:, 1] -= j
+            patches.append((det[i:i1, j:j1].contiguous().cpu().numpy(),
+                            [marks[k, i:i1, j:j1].contiguous().cpu().numpy() for k in range(3)], o))
+    del det_np
+    return patches
+
+
+def make_pool(args, patches):
+    from oracle import cpu_baseline as cb
+    return cb.PatchPool(patches, "legacy", CALIB_HRCM, "hierarchical", HRC, workers=None, t0=args.temperature, alpha_t=1.0)
+
+
+def run_reference(args):
+    """The reference's CPU sampler (oracle port: the reference is pure Python and cannot travel to the GPU box) on all
+    host cores, reference decomposition: one sequential chain per 256^2 patch per process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    patches = cpu_patches(args, device)
+    pool = make_pool(args, patches)
+    per_step = max(200, args.cpu_steps // 4)
+    for _ in range(max(0, min(args.warmup, 1))):
+        pool.run(per_step // 4, seed=args.seed + 1000)
+    tot_p, tot_t = 0, 0.0
+    for s in range(args.steps):
+        p, t, _, _ = pool.run(per_step, seed=args.seed + 17 * s)
+        tot_p += p
+        tot_t += t
+    pool.close()
+    value = tot_p / tot_t
+    sample = f"{pool.workers} workers x {per_step} proposals per step on distinct 256^2 patches of the scene ({args.steps} steps)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "decomposition": "256x256 patches, one sequential chain per host core"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ product arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from mpp_cnn_rs_object_detection_b200 import synth
+    from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec, kernel_probabilities
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (product arm) needs a CUDA device: the MPP sampler has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    h = w = args.size
+    objs, det, marks = synth.make_scene_torch(args.seed + rank, (h, w), n_rect_for(args), device)
+    spec = ModelSpec(setup="legacy", pos_threshold=CALIB_HRCM["detection_threshold"], remap_coefs=CALIB_HRCM["coefs"],
+                     remap_intercepts=CALIB_HRCM["intercepts"], min_area=CALIB_HRCM["min_area"], max_area=CALIB_HRCM["max_area"],
+                     combinator="hierarchical",
+                     comb_w=list(HRC["weights_data"]) + list(HRC["weights_prior"]) + list(HRC["data_prior_weights"]) + [0.0],
+                     comb_bias=HRC["bias"], comb_threshold=HRC["detection_threshold"])
+    eng = Engine((h, w), device=device)
+    eng.set_maps(det, marks)
+    eng.set_model(spec)
+    eng.set_kernels(intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    n0 = len(eng)
+
+    def step(seed_off):
+        eng.run_sweeps(args.sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
+                       sweep_offset=seed_off * args.sweeps, read_counters=False)
+
+    for s in range(args.warmup):
+        step(s)
+    eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)  # reads + resets the counters
+    launches0 = eng.launches
+    clocks = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clk = clocks.stop()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    cnt = eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
+    gpu_launches = eng.launches - launches0
+    proposals = sum_over_ranks(float(cnt[0]))
+    accepted = sum_over_ranks(float(cnt[1]))
+    n1 = len(eng)
+    value = proposals / (ms * 1e-3)
+
+    # ---- e2e: host maps -> device -> sampler -> host configuration
+    e2e = None
+    if not args.no_e2e:
+        det_h = torch.empty(det.shape, dtype=torch.float32, pin_memory=True).copy_(det)
+        marks_h = torch.empty(marks.shape, dtype=torch.float32, pin_memory=True).copy_(marks)
+        det_d, marks_d = torch.empty_like(det), torch.empty_like(marks)
+        xy_h = np.ascontiguousarray(objs[:, :2].astype(np.int32))
+        mk_h = np.ascontiguousarray(objs[:, 2:5])
+        d2h = 0
+
+        def e2e_step(seed_off):
+            nonlocal d2h
+            det_d.copy_(det_h, non_blocking=True)
+            marks_d.copy_(marks_h, non_blocking=True)
+            eng.clear()
+            eng.set_maps(det_d, marks_d)
+            eng.add_objects(xy_h, mk_h)
+            eng.run_sweeps(args.sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
+                           sweep_offset=seed_off * args.sweeps, read_counters=False)
+            hd, xy, mk, uid = eng.read_objects()
+            d2h = hd.nbytes + xy.nbytes + mk.nbytes + uid.nbytes
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step(1000)
+        eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            e2e_step(2000 + s)
+        torch.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        cnt2 = eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
+        p2 = sum_over_ranks(float(cnt2[0]))
+        e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4 + xy_h.nbytes + mk_h.nbytes + 4 * len(xy_h)),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
+               "timer": "host wall clock around H2D + sampler + D2H, max over ranks"}
+        del det_h, marks_h, det_d, marks_d
+
+    # ---- roofline of the dominant kernel (k_sweep)
+    ncell = ((h + 31) // 32) * ((w + 31) // 32)
+    k2 = 25.0 * (0.5 * (n0 + n1)) / ncell
+    acc = accepted / max(1.0, proposals)
+    bpp = bytes_per_proposal(k2, acc, h, w, kernel_probabilities())
+    peak, peak_src = measured_peak()
+    sweep_launches = args.steps * args.sweeps * args.stride * args.stride
+    achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
+                "proposals_per_launch": proposals / world / sweep_launches, "us_per_launch": 1e3 * ms / sweep_launches,
+                "note": "latency/parallelism-bound Markov chain: see DESIGN.md"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "sweeps_per_step": args.sweeps, "proposals_per_visit": args.per_visit,
+                       "colour_stride": args.stride, "objects_start": n0, "objects_end": n1, "acceptance": acc,
+                       "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU",
+                       "l2": "inputs larger than L2 (mark maps 3 x %.0f MB)" % (h * w * 32 * 4 / 1e6)},
+            "ms_per_image": ms / args.steps, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cb
+        patches = []
+        det_c, marks_c = det, marks
+        workers = cb.host_cores()
+        for i in range(0, h, cb.PATCH):
+            for j in range(0, w, cb.PATCH):
+                if len(patches) >= workers:
+                    break
+                i1, j1 = min(h, i + cb.PATCH), min(w, j + cb.PATCH)
+                sel = (objs[:, 0] >= i) & (objs[:, 0] < i1) & (objs[:, 1] >= j) & (objs[:, 1] < j1)
+                o = objs[sel].copy()
+                o[:, 0] -= i
+                o[:, 1] -= j
+                patches.append((det_c[i:i1, j:j1].contiguous().cpu().numpy(),
+                                [marks_c[k, i:i1, j:j1].contiguous().cpu().numpy() for k in range(3)], o))
+        pool = make_pool(args, patches)
+        p, t, a, _ = pool.run(args.cpu_steps, warm=100, seed=args.seed)
+        pool.close()
+        line["cpu_baseline"] = {"value": p / t, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                                "sample": f"{pool.workers} workers x {args.cpu_steps} proposals, one 256^2 patch chain each (reference decomposition), "
+                                          f"T={args.temperature}, acceptance {a / max(1, p):.3f}",
+                                "per_core": p / t / pool.workers}
+    eng.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
