@@ -45,7 +45,13 @@ typedef enum {
 } mpp_status;
 
 typedef enum { MPP_PRECISION_FP32 = 0, MPP_PRECISION_FP64 = 1 } mpp_precision;
-typedef enum { MPP_SETUP_LEGACY = 0, MPP_SETUP_NO_CALIBRATION = 1 } mpp_setup;
+typedef enum {
+    MPP_SETUP_LEGACY = 0,         /* energy_setup_legacy.py:52-86 */
+    MPP_SETUP_NO_CALIBRATION = 1, /* energy_setup_no_calibration.py:56-110 */
+    MPP_SETUP_TOY = 2             /* the toy terms of the reference's own tests (test/test_energy_graph.py:15-35,
+                                     test/test_interacting_points_set.py:24-43): a constant unit energy and a pair
+                                     energy `value if distance <(=) max_dist else 0`, max-reduced; no maps needed */
+} mpp_setup;
 typedef enum {
     MPP_COMB_RAW_SUM = 0,      /* energy_graph.py:132-133 (energy_combinator is None) */
     MPP_COMB_HIERARCHICAL = 1, /* combination/hierarchical.py:21-32 */
@@ -76,6 +82,16 @@ typedef struct {
     double comb_w[MPP_MAX_TERMS];
     double comb_bias;
     double comb_threshold;       /* detection_threshold of the indicator */
+    /* MPP_SETUP_TOY only (term order: Unit, Pair).  The pair exists iff distance <= overlap_max_dist
+     * (energy_graph.py:70-74); its value is toy_pair_value when distance <= toy_pair_dist (toy_pair_strict: <). */
+    double toy_unit_value;
+    double toy_pair_value;
+    double toy_pair_dist;
+    int32_t toy_pair_strict;
+    /* != 0: the mark maps passed to mpp_set_maps already hold energies (the reference's pre-computed
+     * ShapeEnergy.parameter_energy_map / SingleMarkEnergy.parameter_energy_map, data_energies.py:30,51): they are
+     * gathered as they are, without the legacy remap / the no-calibration negation. */
+    int32_t marks_are_energies;
 } mpp_model_params;
 
 /* Proposal-kernel parameters: make_kernels (rjmcmc_sampler/kernels/make_kernels.py:50-177). */
@@ -148,6 +164,16 @@ int mpp_num_objects(mpp_ctx *ctx, int *n_host);  /* synchronises */
 int mpp_read_objects(mpp_ctx *ctx, int capacity, uint32_t *handle, int32_t *xy, double *marks, uint32_t *uid,
                      int *n_host);
 
+/* PointsSet.get_potential_neighbors (point_set.py:111-145): every object of the cells within ceil(radius / 32)
+ * cell offsets of the cell of (x, y), except `exclude_handle` (MPP_NO_OBJECT: none).  euclidean != 0 adds the
+ * distance filter of get_neighbors (point_set.py:147-149).  out_handle holds `capacity` entries; *n_host receives
+ * the number found (may exceed capacity: then only the first `capacity` were written).  Synchronises. */
+int mpp_query_neighbors(mpp_ctx *ctx, int x, int y, double radius, int euclidean, uint32_t exclude_handle, int capacity,
+                        uint32_t *out_handle, int *n_host);
+/* Device-to-device copy of the object state (PointsSet.__copy__ point_set.py:74-82, EnergyGraph.__copy__
+ * energy_graph.py:92-100).  Both contexts must have the same support shape, precision and device. */
+int mpp_copy_state(mpp_ctx *dst, const mpp_ctx *src);
+
 /* ---------------------------------------------------------------------------------------------- energies
  * EnergyGraph.compute_subset(return_vector=True) (energy_graph.py:108-137) for the objects named by `handle`
  * (n of them): out_vectors [n][MPP_MAX_TERMS] (unused columns 0), out_combined [n] = combinator value of each
@@ -155,6 +181,11 @@ int mpp_read_objects(mpp_ctx *ctx, int capacity, uint32_t *handle, int32_t *xy, 
  * combinator total}.  Any output may be NULL. */
 int mpp_energy_vectors(mpp_ctx *ctx, const uint32_t *handle, int n, double *out_vectors, double *out_combined,
                        double *out_totals);
+
+/* PairEnergy.compute (base_energies.py:77-80) for n pairs of stored objects: out [n][2] = {overlap kind value,
+ * alignment kind value}; an entry is NaN when the pair does not exist for that kind (distance > max_dist,
+ * energy_graph.py:70-74). */
+int mpp_pair_values(mpp_ctx *ctx, const uint32_t *handle_a, const uint32_t *handle_b, int n, double *out);
 
 /* EPointsSet.energy_delta (energy_point_set.py:83-100 -> energy_graph.py:139-225) for m independent
  * perturbations against the current state (none is applied).  Only rem_* / add_* of each proposal are read.
@@ -167,6 +198,27 @@ int mpp_delta_batch(mpp_ctx *ctx, const mpp_proposal *props, int m, double *out_
  * step while > t_target (rjmcmc.py:158-159).  out [m]. */
 int mpp_replay(mpp_ctx *ctx, const mpp_proposal *props, int m, double t0, double alpha_t, double t_target,
                mpp_step_result *out);
+
+/* Device-resident sequential chain: RJMCMC.run (rjmcmc.py:83-181) with the reference's eight global kernels
+ * (make_kernels.py:88-144: uniform pick among all objects point_set.py:176-185, global births, Lambda = intensity)
+ * and Philox4x32-10 in place of the numpy Generator.  One proposal at a time, strictly in order, on one warp.
+ * trace (device, n_steps entries) may be NULL; counters_host[4] as in mpp_run_sweeps (may be NULL). */
+int mpp_run_chain(mpp_ctx *ctx, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed,
+                  uint64_t step_offset, mpp_step_result *trace, unsigned long long *counters_host);
+
+/* Kernel.sample_perturbation (base_kernels.py:18-20 and subclasses) for m independent draws against the current
+ * state (nothing is applied): kernel_ids [m] (device; entry < 0: the kernel itself is drawn with p_kernel,
+ * rjmcmc.py:88) -> out [m] proposals (device) whose `u` field holds a fresh accept uniform. */
+int mpp_sample_proposals(mpp_ctx *ctx, const int32_t *kernel_ids, int m, uint64_t seed, uint64_t offset, mpp_proposal *out);
+
+/* Kernel.forward_probability / backward_probability (base_kernels.py:22-28) of m proposals against the current
+ * state: out [m][2] = {forward, backward}. */
+int mpp_proposal_probs(mpp_ctx *ctx, const mpp_proposal *props, int m, double *out);
+
+/* EnergyCombinationModel.compute (custom_types/energy.py:8-11) on device for n per-object energy vectors
+ * [n][MPP_MAX_TERMS] (term order of the setup): out_per_object [n] (may be NULL), out_total [1].  No ctx needed. */
+int mpp_combine(const mpp_model_params *model_host, const double *vectors, int n, double *out_per_object,
+                double *out_total, int device, void *stream);
 
 /* Parallel sampler (new; replaces the sequential loop RJMCMC.run rjmcmc.py:172-181).  Each sweep visits the
  * `stride`^2 colour classes of the cell grid once; every active cell performs `proposals_per_visit` local

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmpp_b200.so")
 NO_OBJECT = 0xFFFFFFFF
 MAX_TERMS = 8
 PRECISION_FP32, PRECISION_FP64 = 0, 1
-SETUP_LEGACY, SETUP_NO_CALIBRATION = 0, 1
+SETUP_LEGACY, SETUP_NO_CALIBRATION, SETUP_TOY = 0, 1, 2
 COMB_RAW_SUM, COMB_HIERARCHICAL, COMB_LOGISTIC, COMB_MANUAL_HIERARCHICAL = 0, 1, 2, 3
 
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OUT_OF_BOUNDS, ERR_CELL_FULL, ERR_NEIGHBOURHOOD, ERR_NOT_FOUND = -1, -2, -3, -4, -5, -6, -7
@@ -24,7 +24,9 @@ class ModelParams(C.Structure):
                 ("pos_threshold", C.c_double), ("remap_coef", C.c_double * 3), ("remap_intercept", C.c_double * 3),
                 ("min_area", C.c_double), ("max_area", C.c_double), ("target_ratio", C.c_double),
                 ("overlap_max_dist", C.c_double), ("align_max_dist", C.c_double), ("comb_w", C.c_double * MAX_TERMS),
-                ("comb_bias", C.c_double), ("comb_threshold", C.c_double)]
+                ("comb_bias", C.c_double), ("comb_threshold", C.c_double), ("toy_unit_value", C.c_double),
+                ("toy_pair_value", C.c_double), ("toy_pair_dist", C.c_double), ("toy_pair_strict", C.c_int32),
+                ("marks_are_energies", C.c_int32)]
 
 
 class KernelParams(C.Structure):
@@ -44,7 +46,9 @@ STEP_RESULT_DTYPE = np.dtype([("delta_e", "<f8"), ("fwd", "<f8"), ("bwd", "<f8")
 SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_create", "mpp_ctx_destroy", "mpp_set_maps",
            "mpp_set_model", "mpp_set_kernels", "mpp_add_objects", "mpp_remove_objects", "mpp_clear_objects",
            "mpp_num_objects", "mpp_read_objects", "mpp_energy_vectors", "mpp_delta_batch", "mpp_replay",
-           "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows"]
+           "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
+           "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
+           "mpp_proposal_probs", "mpp_combine"]
 
 _lib = None
 
@@ -87,6 +91,13 @@ def load():
     lib.mpp_naive_init.argtypes = [vp, f64, f64, C.POINTER(i32)]
     lib.mpp_pack_rows.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
     lib.mpp_unpack_rows.argtypes = [vp, i32, i32, vp, i32]
+    lib.mpp_query_neighbors.argtypes = [vp, i32, i32, f64, i32, C.c_uint32, i32, vp, C.POINTER(i32)]
+    lib.mpp_copy_state.argtypes = [vp, vp]
+    lib.mpp_pair_values.argtypes = [vp, vp, vp, i32, vp]
+    lib.mpp_run_chain.argtypes = [vp, i32, f64, f64, f64, u64, u64, vp, C.POINTER(C.c_ulonglong)]
+    lib.mpp_sample_proposals.argtypes = [vp, vp, i32, u64, u64, vp]
+    lib.mpp_proposal_probs.argtypes = [vp, vp, i32, vp]
+    lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")
     sizes = [C.sizeof(ModelParams), C.sizeof(KernelParams), PROPOSAL_DTYPE.itemsize, STEP_RESULT_DTYPE.itemsize]

@@ -1,0 +1,282 @@
+"""The Metropolis-Hastings-Green loop and its entry function: models/mpp/rjmcmc_sampler/{rjmcmc,sample_rjmcmc,
+stopping}.py and utils/nms.py:68-109.
+
+Three execution modes, all on the device:
+  * RJMCMC.step()            one proposal per call through the Kernel objects (any Kernel subclass works);
+  * RJMCMC.run()             with the built-in kernels and StopOnMaxIter: the whole sequential chain in one kernel
+                             (mpp_run_chain: the reference's algorithm, global kernels, Philox randomness);
+  * sample_rjmcmc(..., sampler='parallel')  the colour-sweep sampler (mpp_run_sweeps): same target distribution and
+                             the same proposal budget / temperature trajectory, cells sampled concurrently."""
+from __future__ import annotations
+
+import logging
+import time
+import warnings
+from dataclasses import dataclass
+from typing import Callable, List, Tuple, Union
+
+import numpy as np
+
+from .custom_types import EnergyCombinationModel, ImageWMaps, RJMCMCStateSummary
+from .energy_point_set import EPointsSet
+from .energy_setups import EnergySetup
+from .kernels import DeviceKernel, Kernel, make_kernels
+from .shapes import Rectangle
+
+EPS = 1e-16  # rjmcmc.py:15
+
+
+# ---------------------------------------------------------------------------------------------- stopping.py
+class StoppingCondition:
+    def do_stop(self, states: List[RJMCMCStateSummary]) -> bool:
+        raise NotImplementedError
+
+    def print(self, states: List[RJMCMCStateSummary]) -> str:
+        return ""
+
+
+class StopOnMaxIter(StoppingCondition):  # stopping.py:37-45
+    def __init__(self, max_iter: int):
+        self.max_iter = max_iter
+
+    def do_stop(self, states: List[RJMCMCStateSummary]) -> bool:
+        return states[-1].iter >= self.max_iter
+
+    def print(self, states: List[RJMCMCStateSummary]) -> str:
+        return f"{states[-1].iter} < {self.max_iter}"
+
+
+# ---------------------------------------------------------------------------------------------- rjmcmc.py
+@dataclass
+class RJMCMC:
+    t0: float
+    kernels: List[Kernel]
+    p_kernels: List[float]
+    initial_state: EPointsSet
+    stopping_condition: StoppingCondition
+    rng: np.random.Generator
+    energy_combinator: EnergyCombinationModel = None
+    t_target: float = 0
+    sampling_rule: Callable[[int], bool] = None
+    do_annealing = True
+    alpha_t: float = None
+    verbose: int = 0
+
+    def __post_init__(self):
+        assert len(self.kernels) == len(self.p_kernels)
+        assert (not self.do_annealing) or (self.alpha_t is not None)
+        assert self.t0 >= self.t_target
+        self._temp: float = self.t0
+        self._iter: int = 0
+        self._state_log: List[EPointsSet] = [self.initial_state]
+        self._state_summaries: List[RJMCMCStateSummary] = [RJMCMCStateSummary(n_points=len(self.initial_state), iter=self._iter)]
+
+    def step(self, return_state=False):
+        """One Metropolis-Hastings-Green step (rjmcmc.py:83-164)."""
+        if self.stopping_condition.do_stop(self._state_summaries):
+            raise StopIteration
+        k1: Kernel = self.kernels[int(self.rng.choice(len(self.kernels), p=self.p_kernels))]
+        x0 = self._state_log[-1]
+        u1 = k1.sample_perturbation(x0.points, self.rng)
+        energy_x0 = self._state_summaries[-1].energy
+        if energy_x0 is None:
+            energy_x0 = x0.total_energy()  # raw sum on the first iteration (rjmcmc.py:96-98)
+        energy_delta = x0.energy_delta(u1, energy_combinator=self.energy_combinator)
+        energy_x1 = energy_x0 + energy_delta
+        log_alpha_1 = (-energy_delta / self._temp) + np.log(k1.backward_probability(x0.points, u1) + EPS) \
+            - np.log(k1.forward_probability(x0.points, u1) + EPS)
+        accepted = bool(np.log(self.rng.random() + EPS) < log_alpha_1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            alpha_1 = float(np.exp(log_alpha_1))
+        x1 = x0.apply_perturbation(u1, inplace=True) if accepted else x0
+        summary = RJMCMCStateSummary(iter=self._iter, temperature=self._temp, energy=energy_x1 if accepted else energy_x0,
+                                     n_points=len(x1), kernel=k1.__class__, move_accepted=accepted, alpha=alpha_1,
+                                     initial_energy=energy_x0, proposed_energy=energy_x1)
+        self._state_summaries.append(summary)
+        if self.sampling_rule is not None and self.sampling_rule(self._iter):
+            self._state_log.append(x1.copy())
+        else:
+            self._state_log[0] = x1
+        self._iter += 1
+        if self.do_annealing and self._temp > self.t_target:
+            self._temp *= self.alpha_t
+        if return_state:
+            return summary, x1.copy()
+        return summary
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return self.step()
+
+    # -- whole-chain fast path -------------------------------------------------------------------------
+    def _device_chain_possible(self) -> bool:
+        if not isinstance(self.stopping_condition, StopOnMaxIter) or len(self.kernels) != 8:
+            return False
+        if not all(isinstance(k, DeviceKernel) and k.KERNEL_ID == i for i, k in enumerate(self.kernels)):
+            return False
+        if len({id(k._kset) for k in self.kernels}) != 1:
+            return False
+        return self.energy_combinator is None or hasattr(self.energy_combinator, "device_params")
+
+    def _run_on_device(self):
+        x = self._state_log[-1]
+        st = x._state
+        kset = self.kernels[0]._kset
+        kset.p_kernels = np.asarray(self.p_kernels, dtype=np.float64)
+        kset.bind(x.points)
+        st.use_combinator(self.energy_combinator)
+        total = self.stopping_condition.max_iter + 1 - self._iter  # StopOnMaxIter runs max_iter + 1 steps (stopping.py:42)
+        seed = int(self.rng.integers(0, 2 ** 62))
+        alpha = self.alpha_t if self.do_annealing else 1.0
+        names = [k.__class__ for k in self.kernels]
+        done = 0
+        while done < total:
+            # run up to (and including) the next step at which sampling_rule asks for a snapshot
+            seg_end = total
+            if self.sampling_rule is not None:
+                for s in range(done, total):
+                    if self.sampling_rule(self._iter + (s - done)):
+                        seg_end = s + 1
+                        break
+            n = seg_end - done
+            _, trace = st.engine.run_chain(n, t0=self._temp, alpha_t=alpha, t_target=self.t_target, seed=seed, step_offset=self._iter,
+                                           trace=True)
+            for row in trace:
+                self._state_summaries.append(RJMCMCStateSummary(
+                    iter=self._iter, temperature=float(row["temperature"]), n_points=int(row["n_after"]), move_accepted=bool(row["accepted"]),
+                    alpha=float(np.exp(min(row["log_alpha"], 700.0)))))
+                self._iter += 1
+                if self.do_annealing and self._temp > self.t_target:
+                    self._temp *= self.alpha_t
+            st.refresh_from_device()
+            x.energy_graph._members = dict.fromkeys(st.handle_of)
+            done = seg_end
+            if self.sampling_rule is not None and self.sampling_rule(self._iter - 1):
+                self._state_log.append(x.copy())
+        del names
+
+    def run(self, show_timing=False) -> Tuple[Union[List[EPointsSet], EPointsSet], List[RJMCMCStateSummary]]:
+        if self._device_chain_possible() and self.verbose == 0:
+            self._run_on_device()
+        else:
+            for _ in self.__iter__():
+                pass
+        return self._state_log, self._state_summaries
+
+
+# ---------------------------------------------------------------------------------------------- utils/nms.py:68-109
+def nms_distance(centers, confidence_score, threshold, return_index=False):
+    """Greedy distance NMS (highest score first; everything within `threshold` of a picked centre is dropped).
+    Host-side helper kept for API compatibility; sample_rjmcmc's 'naive' init runs mpp_naive_init on the device."""
+    if len(centers) == 0:
+        return ([], [], []) if return_index else ([], [])
+    centers = np.asarray(centers)
+    score = np.asarray(confidence_score)
+    order = np.argsort(score)
+    picked = []
+    while order.size > 0:
+        idx = order[-1]
+        picked.append(idx)
+        d = np.linalg.norm(centers[idx] - centers[order[:-1]], axis=-1)
+        order = order[:-1][d > threshold]
+    pc, ps = [centers[i] for i in picked], [confidence_score[i] for i in picked]
+    return (pc, ps, picked) if return_index else (pc, ps)
+
+
+def naive_detection(image_data: ImageWMaps, detection_threshold: float, energy_setup: EnergySetup = None) -> List[Rectangle]:
+    """Threshold -> greedy 6-px NMS -> argmax marks (sample_rjmcmc.py:23-35), on the device (mpp_naive_init)."""
+    from .energy_setups import LegacyEnergiesCalibration, LegacyEnergySetup
+    if energy_setup is None:
+        energy_setup = LegacyEnergySetup(energy_calibration=LegacyEnergiesCalibration(detection_threshold, [1, 1, 1], [0, 0, 0], 0, 1e30))
+    unit, pair = energy_setup.make_energies(image_data)
+    pts = EPointsSet([], image_data.shape, unit, pair)
+    pts._state.engine.naive_init(float(detection_threshold), 6.0)
+    pts._state.refresh_from_device()
+    return list(pts._state.objects())
+
+
+# ---------------------------------------------------------------------------------------------- sample_rjmcmc.py
+def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples: int, energy_combinator: EnergyCombinationModel,
+                  init_config: Union[str, List[Rectangle], None], init_temperature: float, alpha_t: Union[float, str], burn_in: int,
+                  energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
+                  iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
+                  proposals_per_visit: int = 8, colour_stride: int = 3, precision: str = "fp32"):
+    """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
+
+    sampler='parallel'   colour-sweep sampler: max_iter + 1 proposals in total, spread over ceil(.. / (cells * per_visit))
+                         sweeps; the temperature follows the reference's geometric schedule as a function of the number of
+                         proposals made (one multiplication by alpha_t ** proposals_per_sweep per sweep).
+    sampler='sequential' the reference's one-proposal-at-a-time chain, run on the device."""
+    if use_split_merge:
+        raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
+    unit_energies, pair_energies = energy_setup.make_energies(image_data)
+    points = EPointsSet(points=[], support_shape=image_data.shape, unit_energies_constructors=unit_energies,
+                        pair_energies_constructors=pair_energies, precision=precision)
+    st = points._state
+    if isinstance(init_config, str) and init_config == "gt":
+        st.add_many(image_data.gt_config)
+    elif isinstance(init_config, str) and init_config == "naive":
+        st.engine.naive_init(float(energy_setup.detection_threshold), 6.0)
+        st.refresh_from_device()
+    elif init_config is not None:
+        st.add_many(list(init_config))
+    points.energy_graph._members = dict.fromkeys(st.handle_of)
+
+    if iter_multiplier is not None:  # sample_rjmcmc.py:58-61
+        burn_in = burn_in * iter_multiplier
+        samples_interval = samples_interval * iter_multiplier
+        alpha_t = np.power(alpha_t, 1 / iter_multiplier)
+    if isinstance(alpha_t, str) and alpha_t == "auto":  # :63-66
+        alpha_t = np.power(target_temperature / init_temperature, 1 / burn_in)
+        target_temperature = 0
+    burn_in, samples_interval = int(burn_in), int(samples_interval)
+    intensity = max(1, len(st))  # :68
+    kernels, p_kernels = make_kernels(image_data, intensity=intensity, rng=rng, use_split_merge=use_split_merge)
+    max_iter = burn_in + (num_samples + 1) * samples_interval  # :78
+    start = time.perf_counter()
+    if sampler == "sequential":
+        chain = RJMCMC(t0=init_temperature, t_target=target_temperature, alpha_t=alpha_t, kernels=kernels, p_kernels=p_kernels,
+                       initial_state=points, energy_combinator=energy_combinator, stopping_condition=StopOnMaxIter(max_iter), rng=rng,
+                       sampling_rule=lambda step: step >= burn_in and step % samples_interval == 0, verbose=verbose)
+        states, _ = chain.run()
+        result = [states[-1].points] if num_samples == 1 else [s.points for s in states[-num_samples:]]
+    elif sampler == "parallel":
+        kernels[0]._kset.bind(points.points)
+        st.use_combinator(energy_combinator)
+        eng = st.engine
+        ncell = ((image_data.shape[0] + 31) // 32) * ((image_data.shape[1] + 31) // 32)
+        per_sweep = ncell * int(proposals_per_visit)
+        seed = int(rng.integers(0, 2 ** 62))
+        # snapshot steps of the reference's sampling_rule, expressed in sweeps
+        snap_steps = [s for s in range(burn_in, max_iter + 1) if s % samples_interval == 0] if samples_interval > 0 else []
+        snap_sweeps = sorted({-(-(s + 1) // per_sweep) for s in snap_steps})
+        total_sweeps = -(-(max_iter + 1) // per_sweep)
+        alpha_sweep = float(np.power(alpha_t, per_sweep))
+        temp, done, states = float(init_temperature), 0, []
+        for stop in snap_sweeps + ([total_sweeps] if (not snap_sweeps or snap_sweeps[-1] < total_sweeps) else []):
+            n = stop - done
+            if n > 0:
+                eng.run_sweeps(n, proposals_per_visit, colour_stride, t0=temp, alpha_t=alpha_sweep, t_target=float(target_temperature),
+                               seed=seed, sweep_offset=done, read_counters=False)
+                for _ in range(n):
+                    if temp > target_temperature:
+                        temp *= alpha_sweep
+                done = stop
+            if stop in snap_sweeps:
+                st.refresh_from_device()
+                points.energy_graph._members = dict.fromkeys(st.handle_of)
+                states.append(points.copy())
+        st.refresh_from_device()
+        points.energy_graph._members = dict.fromkeys(st.handle_of)
+        if not states:
+            states = [points]
+        result = [states[-1].points] if num_samples == 1 else [s.points for s in states[-num_samples:]]
+    else:
+        raise ValueError(f"sampler must be 'parallel' or 'sequential', got {sampler!r}")
+    end = time.perf_counter()
+    logging.info(f"rjmcmc on image {image_data.name} ran in {end - start:.2f}s ({(end - start) / max(1, max_iter):.1e}s/iter) "
+                 f"(int. {intensity} | iter {max_iter} | num_samples {num_samples} | {sampler})")
+    return result

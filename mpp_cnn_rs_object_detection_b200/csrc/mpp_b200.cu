@@ -11,6 +11,7 @@
 
 #include "mpp_device.cuh"
 #include "mpp_proposals.cuh"
+#include "mpp_chain.cuh"
 
 // ================================================================================================ host ctx
 struct mpp_ctx {
@@ -23,6 +24,7 @@ struct mpp_ctx {
     double *d_cell_cdf = nullptr;
     int *d_scan = nullptr;              // [ncell + 1] exclusive prefix of per-cell populations
     int *d_nobj = nullptr;
+    int *d_rowcount = nullptr;          // [nx] objects per row of cells (global uniform pick)
     uint32_t *d_next_uid = nullptr;
     uint32_t *d_err = nullptr;
     unsigned long long *d_counters = nullptr;
@@ -305,6 +307,147 @@ __global__ void k_replay(Ctx<R> c, const mpp_proposal *__restrict__ props, int m
     if (lane == 0) *c.n_objects = n;
 }
 
+// ---- sequential device chain with the reference's global kernels (R15-R21) ---------------------------
+__global__ void k_row_counts(const uint32_t *__restrict__ mask, int nx, int ny, int *__restrict__ row_count, int *__restrict__ n_objects) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nx) return;
+    int s = 0;
+    for (int j = lane; j < ny; j += 32) s += __popc(mask[row * ny + j]);
+    s = warp_sum(s);
+    if (lane == 0) { row_count[row] = s; if (n_objects) atomicAdd(n_objects, s); }
+}
+
+template <typename R>
+__device__ __forceinline__ void fill_proposal(mpp_proposal *p, int kernel, const Drawn<R> &d, double u) {
+    p->kernel = kernel;
+    p->rem_x = d.has_rem ? d.rem.x : 0; p->rem_y = d.has_rem ? d.rem.y : 0;
+    p->rem_uid = d.has_rem ? d.rem.uid : MPP_NO_OBJECT;
+    p->add_x = d.has_add ? d.add.x : 0; p->add_y = d.has_add ? d.add.y : 0;
+    p->add_uid = d.has_add ? 0u : MPP_NO_OBJECT;
+    p->add_cls = d.has_add ? d.add.cls : 0u;
+    p->add_size = d.has_add ? (double)d.add.size : 0.0;
+    p->add_ratio = d.has_add ? (double)d.add.ratio : 0.0;
+    p->add_angle = d.has_add ? (double)d.add.angle : 0.0;
+    p->delta0 = d.d0; p->delta1 = d.d1; p->param_id = d.param_id; p->new_class = d.new_class; p->u = u;
+}
+
+template <typename R>
+__global__ void k_sample_proposals(Ctx<R> c, const int *__restrict__ row_count, const int32_t *__restrict__ kernel_ids, int m,
+                                   uint64_t seed, uint64_t offset, mpp_proposal *__restrict__ out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= m) return;
+    const uint64_t id = offset + (uint64_t)i;
+    Philox rng(seed, (uint32_t)id, (uint32_t)(id >> 32), 0x5a3du);
+    const uint4 r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
+    const int n = __ldcg(c.n_objects);
+    int kernel = kernel_ids ? kernel_ids[i] : -1;
+    if (kernel < 0 || kernel > 7) kernel = draw_kernel(c.k, u01(r0.x, r0.y));
+    Drawn<R> d;
+    draw_global(c, row_count, n, kernel, r0, r1, r2, lane, &d);
+    if (lane == 0) fill_proposal(out + i, kernel, d, u01(r2.z, r2.w));
+}
+
+template <typename R>
+__global__ void k_proposal_probs(Ctx<R> c, const mpp_proposal *__restrict__ props, int m, double *__restrict__ out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= m) return;
+    const mpp_proposal p = props[i];
+    bool has_rem, has_add;
+    uint32_t rh;
+    Rec<R> rem, add;
+    double fwd = 0, bwd = 0;
+    if (resolve_proposal(c, p, lane, &has_rem, &rh, &rem, &has_add, &add))
+        proposal_probs(c, p.kernel, has_rem, rem, has_add, add, p.delta0, p.delta1, p.param_id, p.new_class,
+                       (double)__ldcg(c.n_objects), c.k.intensity, lane, &fwd, &bwd);
+    if (lane == 0) { out[2 * i] = fwd; out[2 * i + 1] = bwd; }
+}
+
+template <typename R>
+__global__ void k_run_chain(Ctx<R> c, int *__restrict__ row_count, int n_steps, double t0, double alpha_t, double t_target,
+                            uint64_t seed, uint64_t step_offset, mpp_step_result *__restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Scratch<R> &s = *reinterpret_cast<Scratch<R> *>(smem);
+    const int lane = threadIdx.x & 31;
+    int n = __ldcg(c.n_objects);
+    double temp = t0;
+    unsigned n_acc = 0, n_birth = 0, n_death = 0;
+    for (int step = 0; step < n_steps; ++step) {
+        const uint64_t id = step_offset + (uint64_t)step;
+        Philox rng(seed, (uint32_t)id, (uint32_t)(id >> 32), 0xc4a1u);
+        const uint4 r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
+        const int kernel = draw_kernel(c.k, u01(r0.x, r0.y));
+        Drawn<R> d;
+        draw_global(c, row_count, n, kernel, r0, r1, r2, lane, &d);
+        bool valid = true;
+        if (d.has_add) {  // capacity of the destination cell (MPP_CELL_CAPACITY slots)
+            uint32_t dm = __ldcg(c.mask + cell_of(c, d.add.x, d.add.y));
+            if (d.has_rem && (d.rem_handle >> 5) == (uint32_t)cell_of(c, d.add.x, d.add.y)) dm &= ~(1u << (d.rem_handle & 31));
+            if (dm == 0xffffffffu) { valid = false; if (lane == 0) atomicOr(c.err, ERRF_CELL_FULL); }
+        }
+        double de = 0, fwd = 0, bwd = 0, la = 0;
+        bool acc = false;
+        if (valid) {
+            de = (double)warp_delta(c, s, d.has_rem, d.rem_handle, d.rem, d.has_add, d.add, lane);
+            proposal_probs(c, kernel, d.has_rem, d.rem, d.has_add, d.add, d.d0, d.d1, d.param_id, d.new_class, (double)n,
+                           c.k.intensity, lane, &fwd, &bwd);
+            la = (-de / temp) + log(bwd + MPP_EPS) - log(fwd + MPP_EPS);      // rjmcmc.py:105-107
+            acc = log(u01(r2.z, r2.w) + MPP_EPS) < la;                        // rjmcmc.py:113
+            if (acc) {
+                if (d.has_rem) {
+                    erase_handle(c, d.rem_handle, lane);
+                    if (lane == 0) row_count[d.rem.x >> 5] -= 1;
+                    --n;
+                }
+                __syncwarp();
+                if (d.has_add) {
+                    if (lane == 0) d.add.uid = atomicAdd(c.next_uid, 1u);
+                    d.add.uid = __shfl_sync(MPP_FULL, d.add.uid, 0);
+                    insert_rec(c, d.add, lane);
+                    if (lane == 0) row_count[d.add.x >> 5] += 1;
+                    ++n;
+                }
+                __threadfence();
+                __syncwarp();
+                ++n_acc;
+                if (d.has_add && !d.has_rem) ++n_birth;
+                if (d.has_rem && !d.has_add) ++n_death;
+            }
+        }
+        if (trace && lane == 0) {
+            mpp_step_result res;
+            res.delta_e = de; res.fwd = fwd; res.bwd = bwd; res.log_alpha = la; res.temperature = temp;
+            res.accepted = acc ? 1 : 0; res.n_after = n;
+            trace[step] = res;
+        }
+        if (temp > t_target) temp *= alpha_t;  // rjmcmc.py:158-159
+    }
+    if (lane == 0) {
+        *c.n_objects = n;
+        atomicAdd(c.counters + 0, (unsigned long long)n_steps);
+        atomicAdd(c.counters + 1, (unsigned long long)n_acc);
+        atomicAdd(c.counters + 2, (unsigned long long)n_birth);
+        atomicAdd(c.counters + 3, (unsigned long long)n_death);
+    }
+}
+
+// ---- R14: combinator over given energy vectors ------------------------------------------------------
+__global__ void k_combine(ModelDev m, const double *__restrict__ vectors, int n, double *__restrict__ out_per, double *__restrict__ out_total) {
+    __shared__ double part[256];
+    const int t = threadIdx.x;
+    double acc = 0.0;
+    for (int i = t; i < n; i += blockDim.x) {
+        double v[MPP_MAX_TERMS];
+        for (int k = 0; k < MPP_MAX_TERMS; ++k) v[k] = vectors[(size_t)i * MPP_MAX_TERMS + k];
+        const double e = combine_v<double>(m, v);
+        if (out_per) out_per[i] = e;
+        acc += e;
+    }
+    part[t] = acc;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) { if (t < o) part[t] += part[t + o]; __syncthreads(); }
+    if (t == 0 && out_total) *out_total = part[0];
+}
+
 // ---- K5 test entry: draw births from the data-driven sampler ---------------------------------------
 template <typename R>
 __global__ void k_sample_births(Ctx<R> c, int n, uint64_t seed, int32_t *__restrict__ out) {
@@ -321,14 +464,6 @@ __global__ void k_sample_births(Ctx<R> c, int n, uint64_t seed, int32_t *__restr
 }
 
 // ---- K6: parallel sweep over one colour class (warp per active cell) -------------------------------
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, uint32_t cc, uint32_t d, double *n0, double *n1) {
-    const double u1 = u01(a, b), u2 = u01(cc, d);
-    const double r = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    *n0 = r * cs; *n1 = r * sn;
-}
-
 template <typename R>
 __global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj, int per_visit, double temp,
                         uint64_t seed, uint64_t sweep_id) {
@@ -479,6 +614,57 @@ __global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj
         atomicAdd(c.counters + 2, (unsigned long long)n_birth);
         atomicAdd(c.counters + 3, (unsigned long long)n_death);
         if (dn) atomicAdd(c.n_objects, dn);
+    }
+}
+
+// ---- R4: neighbour query (PointsSet.get_potential_neighbors / get_neighbors, point_set.py:111-149) ----------
+template <typename R>
+__global__ void k_query_neighbors(Ctx<R> c, int x, int y, int max_offset, long long r2, int euclidean, uint32_t exclude,
+                                  int capacity, uint32_t *__restrict__ out, int *__restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int iu = x >> 5, ju = y >> 5;
+    const int i0 = max(iu - max_offset, 0), i1 = min(iu + max_offset, c.nx - 1);
+    const int j0 = max(ju - max_offset, 0), j1 = min(ju + max_offset, c.ny - 1);
+    int total = 0;
+    for (int i = i0; i <= i1; ++i)
+        for (int j = j0; j <= j1; ++j) {
+            const int cell = j + i * c.ny;
+            const uint32_t msk = c.mask[cell];
+            bool in = (msk >> lane) & 1u;
+            const uint32_t h = (uint32_t)cell * 32u + lane;
+            if (in && h == exclude) in = false;
+            if (in && euclidean) {
+                const Rec<R> *p = c.recs + h;
+                const long long dx = p->x - x, dy = p->y - y;
+                in = dx * dx + dy * dy <= r2;
+            }
+            const uint32_t b = __ballot_sync(MPP_FULL, in);
+            if (in) { const int pos = total + __popc(b & ((1u << lane) - 1)); if (pos < capacity) out[pos] = h; }
+            total += __popc(b);
+        }
+    if (lane == 0) *count = total;
+}
+
+template <typename R>
+__global__ void k_pair_values(Ctx<R> c, const uint32_t *__restrict__ ha, const uint32_t *__restrict__ hb, int n,
+                              double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Scratch<R> &s = reinterpret_cast<Scratch<R> *>(smem)[wib];
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (i >= n) return;
+    const uint32_t a = ha[i], b = hb[i];
+    const bool ok = (a >> 5) < (uint32_t)c.ncell && (b >> 5) < (uint32_t)c.ncell && ((c.mask[a >> 5] >> (a & 31)) & 1u) &&
+                    ((c.mask[b >> 5] >> (b & 31)) & 1u);
+    if (!ok) { if (lane == 0) { atomicOr(c.err, ERRF_NOT_FOUND); out[2 * i] = nan(""); out[2 * i + 1] = nan(""); } return; }
+    const Rec<R> ra = load_rec(c.recs + a), rb = load_rec(c.recs + b);
+    const int dx = ra.x - rb.x, dy = ra.y - rb.y, d2 = dx * dx + dy * dy;
+    const Geo<R> ga = geo_of(ra), gb = geo_of(rb);
+    const R ov = d2 <= c.m.ov_d2 ? pair_overlap(c.m, ga, gb, d2, s.clipx + lane, s.clipy + lane) : (R)0;
+    if (lane == 0) {
+        out[2 * i] = d2 <= c.m.ov_d2 ? (double)ov : nan("");
+        const R al = (c.m.rewarding ? (R)-1 : (R)1) * align_magnitude(ga, gb, c.m.rewarding);
+        out[2 * i + 1] = d2 <= c.m.al_d2 ? (double)al : nan("");
     }
 }
 
@@ -640,6 +826,7 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * h->ncell));
     CUDA_TRY(cudaMalloc(&h->d_scan, sizeof(int) * (h->ncell + 1)));
     CUDA_TRY(cudaMalloc(&h->d_nobj, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_rowcount, sizeof(int) * h->nx));
     CUDA_TRY(cudaMalloc(&h->d_next_uid, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 4));
@@ -659,6 +846,8 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(set_smem(k_delta_batch<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
     CUDA_TRY(set_smem(k_sweep<float>, WARPS_PER_BLOCK * sizeof(Scratch<float>)));
     CUDA_TRY(set_smem(k_sweep<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
+    CUDA_TRY(set_smem(k_pair_values<float>, WARPS_PER_BLOCK * sizeof(Scratch<float>)));
+    CUDA_TRY(set_smem(k_pair_values<double>, WARPS_PER_BLOCK * sizeof(Scratch<double>)));
     CUDA_TRY(set_smem(k_replay<float>, sizeof(Scratch<float>)));
     CUDA_TRY(set_smem(k_replay<double>, sizeof(Scratch<double>)));
     *out = h;
@@ -670,7 +859,7 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_scan); cudaFree(h->d_nobj);
-    cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
+    cudaFree(h->d_rowcount); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
     return MPP_OK;
@@ -696,28 +885,50 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
     return MPP_OK;
 }
 
-int mpp_set_model(mpp_ctx *h, const mpp_model_params *p) {
-    if (!h || !p) return fail(MPP_ERR_INVALID, "mpp_set_model: null argument");
-    if (p->setup != MPP_SETUP_LEGACY && p->setup != MPP_SETUP_NO_CALIBRATION) return fail(MPP_ERR_INVALID, "mpp_set_model: setup");
+}  // extern "C" (helpers)
+
+static int model_from_params(const mpp_model_params *p, ModelDev &m) {
+    if (!p) return fail(MPP_ERR_INVALID, "mpp_set_model: null argument");
+    if (p->setup != MPP_SETUP_LEGACY && p->setup != MPP_SETUP_NO_CALIBRATION && p->setup != MPP_SETUP_TOY)
+        return fail(MPP_ERR_INVALID, "mpp_set_model: setup");
+    if (p->setup == MPP_SETUP_TOY && (p->combinator != MPP_COMB_RAW_SUM || p->toy_pair_value < 0.0))
+        return fail(MPP_ERR_INVALID, "mpp_set_model: the toy setup takes the raw-sum combinator and a non-negative pair value");
     if (p->combinator < 0 || p->combinator > MPP_COMB_MANUAL_HIERARCHICAL) return fail(MPP_ERR_INVALID, "mpp_set_model: combinator");
     if (p->combinator == MPP_COMB_HIERARCHICAL && p->setup != MPP_SETUP_LEGACY)
         return fail(MPP_ERR_INVALID, "hierarchical combinator needs the legacy term names (hierarchical.py:22-29)");
     if (p->overlap_max_dist > MPP_CELL_SIZE || p->align_max_dist > MPP_CELL_SIZE)
         return fail(MPP_ERR_INVALID, "interaction distances above the 32-px cell size are not supported");
-    ModelDev &m = h->m;
     m.setup = p->setup; m.comb = p->combinator; m.ratio_prior = p->ratio_prior; m.rewarding = p->rewarding;
-    m.n_terms = p->setup == MPP_SETUP_LEGACY ? 5 : (p->ratio_prior ? 8 : 7);
-    m.ov_d2 = (int)floor(p->overlap_max_dist * p->overlap_max_dist);
-    m.al_d2 = (int)floor(p->align_max_dist * p->align_max_dist);
+    m.n_terms = p->setup == MPP_SETUP_LEGACY ? 5 : (p->setup == MPP_SETUP_TOY ? 2 : (p->ratio_prior ? 8 : 7));
+    m.ov_d2 = p->overlap_max_dist < 0 ? -1 : (int)floor(p->overlap_max_dist * p->overlap_max_dist);
+    m.al_d2 = (p->setup == MPP_SETUP_TOY || p->align_max_dist < 0) ? -1 : (int)floor(p->align_max_dist * p->align_max_dist);
+    m.premapped = p->marks_are_energies ? 1 : 0;
+    m.toy_unit = p->toy_unit_value; m.toy_pair = p->toy_pair_value;
+    {
+        const double t2 = p->toy_pair_dist * p->toy_pair_dist;
+        m.toy_d2 = p->toy_pair_dist < 0 ? -1 : (p->toy_pair_strict ? (int)ceil(t2) - 1 : (int)floor(t2));
+    }
     m.max_d2 = m.ov_d2 > m.al_d2 ? m.ov_d2 : m.al_d2;
     m.pos_thr = (float)p->pos_threshold;
     for (int i = 0; i < 3; ++i) { m.coef[i] = (float)p->remap_coef[i]; m.icpt[i] = (float)p->remap_intercept[i]; }
     m.min_area = p->min_area; m.max_area = p->max_area; m.target_ratio = p->target_ratio;
     for (int i = 0; i < MPP_MAX_TERMS; ++i) m.w[i] = p->comb_w[i];
     m.bias = p->comb_bias; m.thr = p->comb_threshold;
+    return MPP_OK;
+}
+
+int mpp_set_model(mpp_ctx *h, const mpp_model_params *p) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_set_model: null ctx");
+    ModelDev m;
+    memset(&m, 0, sizeof(m));
+    const int rc = model_from_params(p, m);
+    if (rc != MPP_OK) return rc;
+    h->m = m;
     h->model_set = true;
     return MPP_OK;
 }
+
+extern "C" {
 
 int mpp_set_kernels(mpp_ctx *h, const mpp_kernel_params *p) {
     if (!h || !p) return fail(MPP_ERR_INVALID, "mpp_set_kernels: null argument");
@@ -738,7 +949,7 @@ int mpp_set_kernels(mpp_ctx *h, const mpp_kernel_params *p) {
 
 int mpp_add_objects(mpp_ctx *h, const int32_t *xy, const double *marks, const uint32_t *cls, const uint32_t *uid, int n,
                     uint32_t *out_handle) {
-    NEED(h, h->maps_set && h->model_set, "mpp_add_objects: set maps and model first");
+    NEED(h, h->model_set && (h->maps_set || h->m.setup == MPP_SETUP_TOY), "mpp_add_objects: set maps and model first");
     if (n < 0 || (n > 0 && (!xy || !marks))) return fail(MPP_ERR_INVALID, "mpp_add_objects: bad arguments");
     if (n == 0) return MPP_OK;
     CUDA_TRY(cudaSetDevice(h->device));
@@ -790,8 +1001,52 @@ int mpp_read_objects(mpp_ctx *h, int capacity, uint32_t *handle, int32_t *xy, do
     return MPP_OK;
 }
 
+int mpp_query_neighbors(mpp_ctx *h, int x, int y, double radius, int euclidean, uint32_t exclude_handle, int capacity,
+                        uint32_t *out_handle, int *n_host) {
+    NEED(h, n_host != nullptr, "mpp_query_neighbors: null output");
+    if (capacity < 0 || (capacity > 0 && !out_handle) || radius < 0) return fail(MPP_ERR_INVALID, "mpp_query_neighbors: bad arguments");
+    if (x < 0 || y < 0 || x >= h->H || y >= h->W) return fail(MPP_ERR_OUT_OF_BOUNDS, "object outside the support (point_set.py:99)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int max_offset = (int)ceil(radius / (double)MPP_CELL_SIZE);  // point_set.py:129
+    const long long r2 = (long long)floor(radius * radius);
+    int *count = h->d_scan;
+    DISPATCH(h, (k_query_neighbors<R><<<1, 32, 0, h->stream>>>(device_view<R>(h), x, y, max_offset, r2, euclidean, exclude_handle,
+                                                             capacity, out_handle, count)));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->h_pinned, count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *n_host = *h->h_pinned;
+    return MPP_OK;
+}
+
+int mpp_copy_state(mpp_ctx *dst, const mpp_ctx *src) {
+    if (!dst || !src) return fail(MPP_ERR_INVALID, "mpp_copy_state: null ctx");
+    if (dst->H != src->H || dst->W != src->W || dst->precision != src->precision || dst->device != src->device)
+        return fail(MPP_ERR_INVALID, "mpp_copy_state: contexts differ in shape, precision or device");
+    CUDA_TRY(cudaSetDevice(dst->device));
+    const size_t rec = dst->precision == MPP_PRECISION_FP64 ? sizeof(Rec<double>) : sizeof(Rec<float>);
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_mask, src->d_mask, sizeof(uint32_t) * dst->ncell, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_recs, src->d_recs, rec * (size_t)dst->ncell * MPP_CELL_CAPACITY, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_nobj, src->d_nobj, sizeof(int), cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_next_uid, src->d_next_uid, sizeof(uint32_t), cudaMemcpyDeviceToDevice, dst->stream));
+    return MPP_OK;
+}
+
+int mpp_pair_values(mpp_ctx *h, const uint32_t *handle_a, const uint32_t *handle_b, int n, double *out) {
+    NEED(h, h->model_set, "mpp_pair_values: set the model first");
+    if (n < 0 || (n > 0 && (!handle_a || !handle_b || !out))) return fail(MPP_ERR_INVALID, "mpp_pair_values: bad arguments");
+    if (n == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    DISPATCH(h, (k_pair_values<R><<<blocks, WARPS_PER_BLOCK * 32, WARPS_PER_BLOCK * sizeof(Scratch<R>), h->stream>>>(
+                    device_view<R>(h), handle_a, handle_b, n, out)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
 int mpp_energy_vectors(mpp_ctx *h, const uint32_t *handle, int n, double *out_vectors, double *out_combined, double *out_totals) {
-    NEED(h, h->maps_set && h->model_set, "mpp_energy_vectors: set maps and model first");
+    NEED(h, h->model_set && (h->maps_set || h->m.setup == MPP_SETUP_TOY), "mpp_energy_vectors: set maps and model first");
     if (n < 0 || (n > 0 && !handle)) return fail(MPP_ERR_INVALID, "mpp_energy_vectors: bad arguments");
     if (out_totals && n > 0 && (!out_vectors || !out_combined)) return fail(MPP_ERR_INVALID, "mpp_energy_vectors: totals need both outputs");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -806,7 +1061,7 @@ int mpp_energy_vectors(mpp_ctx *h, const uint32_t *handle, int n, double *out_ve
 }
 
 int mpp_delta_batch(mpp_ctx *h, const mpp_proposal *props, int m, double *out_delta) {
-    NEED(h, h->maps_set && h->model_set, "mpp_delta_batch: set maps and model first");
+    NEED(h, h->model_set && (h->maps_set || h->m.setup == MPP_SETUP_TOY), "mpp_delta_batch: set maps and model first");
     if (m < 0 || (m > 0 && (!props || !out_delta))) return fail(MPP_ERR_INVALID, "mpp_delta_batch: bad arguments");
     if (m == 0) return MPP_OK;
     CUDA_TRY(cudaSetDevice(h->device));
@@ -923,3 +1178,75 @@ int mpp_unpack_rows(mpp_ctx *h, int row_lo, int row_hi, const double *buf, int n
 }
 
 }  // extern "C"
+
+static int refresh_row_counts(mpp_ctx *h) {
+    CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
+    const int blocks = (h->nx + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    k_row_counts<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(h->d_mask, h->nx, h->ny, h->d_rowcount, h->d_nobj);
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+static int read_counters(mpp_ctx *h, unsigned long long *counters_host) {
+    unsigned long long *tmp = reinterpret_cast<unsigned long long *>(h->h_pinned);
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; ++i) counters_host[i] = tmp[i];
+    return check_device_errors(h);
+}
+
+extern "C" int mpp_run_chain(mpp_ctx *h, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed, uint64_t step_offset,
+                  mpp_step_result *trace, unsigned long long *counters_host) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_chain: set maps, model and kernels first");
+    if (n_steps < 0 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_chain: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n_steps > 0) {
+        int rc = refresh_row_counts(h);
+        if (rc != MPP_OK) return rc;
+        DISPATCH(h, (k_run_chain<R><<<1, 32, sizeof(Scratch<R>), h->stream>>>(device_view<R>(h), h->d_rowcount, n_steps, t0, alpha_t,
+                                                                           t_target, seed, step_offset, trace)));
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (counters_host) return read_counters(h, counters_host);
+    return MPP_OK;
+}
+
+extern "C" int mpp_sample_proposals(mpp_ctx *h, const int32_t *kernel_ids, int m, uint64_t seed, uint64_t offset, mpp_proposal *out) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_sample_proposals: set maps, model and kernels first");
+    if (m < 0 || (m > 0 && !out)) return fail(MPP_ERR_INVALID, "mpp_sample_proposals: bad arguments");
+    if (m == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = refresh_row_counts(h);
+    if (rc != MPP_OK) return rc;
+    const int blocks = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    DISPATCH(h, (k_sample_proposals<R><<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(device_view<R>(h), h->d_rowcount, kernel_ids, m,
+                                                                                    seed, offset, out)));
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+extern "C" int mpp_proposal_probs(mpp_ctx *h, const mpp_proposal *props, int m, double *out) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_proposal_probs: set maps, model and kernels first");
+    if (m < 0 || (m > 0 && (!props || !out))) return fail(MPP_ERR_INVALID, "mpp_proposal_probs: bad arguments");
+    if (m == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    DISPATCH(h, (k_proposal_probs<R><<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(device_view<R>(h), props, m, out)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
+extern "C" int mpp_combine(const mpp_model_params *model_host, const double *vectors, int n, double *out_per_object, double *out_total,
+                int device, void *stream) {
+    if (n < 0 || (n > 0 && !vectors) || !out_total) return fail(MPP_ERR_INVALID, "mpp_combine: bad arguments");
+    ModelDev m;
+    memset(&m, 0, sizeof(m));
+    const int rc = model_from_params(model_host, m);
+    if (rc != MPP_OK) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    k_combine<<<1, 256, 0, (cudaStream_t)stream>>>(m, vectors, n, out_per_object, out_total);
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+

@@ -17,19 +17,25 @@ NOCALIB_NAMES = ["PositionEnergy", "SizeEnergy", "RatioEnergy", "AngleEnergy", "
                  "AreaPriorEnergy", "RatioPriorEnergy"]
 
 
-def kernel_probabilities(use_split_merge: bool = False) -> np.ndarray:
+BASE_KERNEL_WEIGHTS = {"bd_weight": 1, "uniform_bd_weight": 1, "data_bd_weight": 2, "ms_weight": 1, "translation_weight": 1,
+                       "gaussian_translation_weight": 1, "data_translation_weight": 2, "transformation_weight": 1,
+                       "gaussian_transformation_weight": 1, "data_transformation_weight": 2}  # make_kernels.py:13-24
+
+
+def kernel_probabilities(use_split_merge: bool = False, weights=None) -> np.ndarray:
     """Kernel choice probabilities of make_kernels (rjmcmc_sampler/kernels/make_kernels.py:13-24,76-86,163-166)."""
     if use_split_merge:
         raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
+    w = BASE_KERNEL_WEIGHTS if weights is None else weights
 
     def normalize(a):
         a = np.array(a, dtype=np.float64)
         return a / np.linalg.norm(a, ord=1)
 
-    p_bd, p_trl, p_trf = normalize([1, 1, 1])
-    p_bd_unif, p_bd_data = normalize([1, 2])
-    p_trl_gaus, p_trl_data = normalize([1, 2])
-    p_trf_gaus, p_trf_data = normalize([1, 2])
+    p_bd, p_trl, p_trf = normalize([w["bd_weight"], w["translation_weight"], w["transformation_weight"]])
+    p_bd_unif, p_bd_data = normalize([w["uniform_bd_weight"], w["data_bd_weight"]])
+    p_trl_gaus, p_trl_data = normalize([w["gaussian_translation_weight"], w["data_translation_weight"]])
+    p_trf_gaus, p_trf_data = normalize([w["gaussian_transformation_weight"], w["data_transformation_weight"]])
     p = np.array([0.5 * p_bd_unif * p_bd, 0.5 * p_bd_unif * p_bd, 0.5 * p_bd_data * p_bd, 0.5 * p_bd_data * p_bd,
                   p_trl * p_trl_gaus, p_trl * p_trl_data, p_trf * p_trf_gaus, p_trf * p_trf_data])
     if abs(1 - np.sum(p)) < 1e-8:
@@ -40,7 +46,7 @@ def kernel_probabilities(use_split_merge: bool = False) -> np.ndarray:
 @dataclass
 class ModelSpec:
     """Host description of the energy model (terms + combinator) sent to mpp_set_model."""
-    setup: str = "legacy"  # 'legacy' | 'nocalib'
+    setup: str = "legacy"  # 'legacy' | 'nocalib' | 'toy'
     pos_threshold: float = 0.0
     remap_coefs: Sequence[float] = (1.0, 1.0, 1.0)
     remap_intercepts: Sequence[float] = (0.0, 0.0, 0.0)
@@ -55,16 +61,28 @@ class ModelSpec:
     comb_w: Sequence[float] = field(default_factory=lambda: [0.0] * 8)
     comb_bias: float = 0.0
     comb_threshold: float = 0.0
+    # 'toy' setup (the reference tests' toy terms): constant unit energy + distance-indicator pair energy
+    toy_unit_value: float = 0.0
+    toy_pair_value: float = 1.0
+    toy_pair_dist: float = -1.0
+    toy_pair_strict: bool = False
+    toy_names: Sequence[str] = ("Unit", "Pair")
+    marks_are_energies: bool = False  # the mark maps already hold energies (reference-style pre-computed maps)
 
     @property
     def names(self):
+        if self.setup == "toy":
+            return list(self.toy_names)
         if self.setup == "legacy":
             return list(LEGACY_NAMES)
         return list(NOCALIB_NAMES if self.ratio_prior else NOCALIB_NAMES[:7])
 
     def to_c(self) -> _lib.ModelParams:
         p = _lib.ModelParams()
-        p.setup = {"legacy": _lib.SETUP_LEGACY, "nocalib": _lib.SETUP_NO_CALIBRATION}[self.setup]
+        p.setup = {"legacy": _lib.SETUP_LEGACY, "nocalib": _lib.SETUP_NO_CALIBRATION, "toy": _lib.SETUP_TOY}[self.setup]
+        p.toy_unit_value, p.toy_pair_value = float(self.toy_unit_value), float(self.toy_pair_value)
+        p.toy_pair_dist, p.toy_pair_strict = float(self.toy_pair_dist), int(self.toy_pair_strict)
+        p.marks_are_energies = int(self.marks_are_energies)
         p.combinator = {"raw": _lib.COMB_RAW_SUM, "hierarchical": _lib.COMB_HIERARCHICAL, "logistic": _lib.COMB_LOGISTIC,
                         "manual": _lib.COMB_MANUAL_HIERARCHICAL}[self.combinator]
         p.ratio_prior = int(self.ratio_prior)
@@ -100,6 +118,42 @@ def classes_of_marks(marks: np.ndarray) -> np.ndarray:
             raise ValueError(f"mark {i} below its mapping's v_min")
         out[:, i] = np.minimum(c, 31)
     return out
+
+
+def combine_on_device(model: ModelSpec, vectors: np.ndarray, device=None):
+    """EnergyCombinationModel.compute on device: vectors [n, T] -> (per-object [n], total)."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("mpp_cnn_rs_object_detection_b200 needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    v = np.asarray(vectors, dtype=np.float64).reshape(len(vectors), -1)
+    n = len(v)
+    full = np.zeros((n, _lib.MAX_TERMS), dtype=np.float64)
+    full[:, :v.shape[1]] = v
+    dv = torch.as_tensor(full).to(dev)
+    per = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+    tot = torch.zeros(1, dtype=torch.float64, device=dev)
+    p = model.to_c()
+    _lib.check(lib.mpp_combine(C.byref(p), dv.data_ptr() if n else None, n, per.data_ptr(), tot.data_ptr(),
+                               dev.index if dev.index is not None else torch.cuda.current_device(),
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return per[:n].cpu().numpy(), float(tot.cpu().item())
+
+
+_EDGES32 = [e.astype(np.float32) for e in _EDGES]
+
+
+def snap_to_edges(marks: np.ndarray) -> np.ndarray:
+    """Marks read back from a float32 device context: a value that is the float32 rounding of a bin lower edge is
+    replaced by the exact float64 edge, i.e. by the value the reference's data-driven kernels would hold
+    (ValueMapping.class_to_value, mappings.py:63-74), so that value_to_class in float64 gives the same class."""
+    m = np.array(marks, dtype=np.float64).reshape(-1, 3)
+    for i in range(3):
+        v32 = m[:, i].astype(np.float32)
+        k = np.clip(np.searchsorted(_EDGES32[i], v32, side="right") - 1, 0, 31)
+        hit = _EDGES32[i][k] == v32
+        m[hit, i] = _EDGES[i][k[hit]]
+    return m
 
 
 class Engine:
@@ -223,7 +277,10 @@ class Engine:
         _lib.check(self.lib.mpp_read_objects(self.ctx, cap, h.data_ptr(), xy.data_ptr(), m.data_ptr(), u.data_ptr(), C.byref(cnt)))
         self.launches += 2
         n = min(cnt.value, cap)
-        return (h[:n].cpu().numpy().view(np.uint32), xy[:n].cpu().numpy(), m[:n].cpu().numpy(), u[:n].cpu().numpy().view(np.uint32))
+        marks = m[:n].cpu().numpy()
+        if self.precision != "fp64":
+            marks = snap_to_edges(marks)
+        return (h[:n].cpu().numpy().view(np.uint32), xy[:n].cpu().numpy(), marks, u[:n].cpu().numpy().view(np.uint32))
 
     # ------------------------------------------------------------------------------------------ energies
     def energy_vectors(self, handles):
@@ -271,6 +328,47 @@ class Engine:
         self.launches += int(n_sweeps) * stride * stride
         return [int(v) for v in cnt] if read_counters else None
 
+    def run_chain(self, n_steps: int, t0: float = 1.0, alpha_t: float = 1.0, t_target: float = 0.0, seed: int = 0,
+                  step_offset: int = 0, trace: bool = False, read_counters: bool = True):
+        """Sequential device chain with the reference's global kernels (RJMCMC.run, rjmcmc.py:83-181)."""
+        tr = torch.zeros((max(n_steps, 1), _lib.STEP_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=self.device) if trace else None
+        cnt = (C.c_ulonglong * 4)()
+        _lib.check(self.lib.mpp_run_chain(self.ctx, int(n_steps), float(t0), float(alpha_t), float(t_target), int(seed),
+                                          int(step_offset), None if tr is None else tr.data_ptr(), cnt if read_counters else None))
+        self.launches += 2 if n_steps > 0 else 0
+        counters = [int(v) for v in cnt] if read_counters else None
+        if trace:
+            return counters, tr.cpu().numpy().view(_lib.STEP_RESULT_DTYPE).reshape(-1)[:n_steps]
+        return counters
+
+    def sample_proposals(self, kernel_ids, seed: int = 0, offset: int = 0) -> np.ndarray:
+        """Kernel.sample_perturbation for each entry of kernel_ids (-1: draw the kernel too) against the current state."""
+        k = np.ascontiguousarray(np.asarray(kernel_ids, dtype=np.int32).reshape(-1))
+        m = len(k)
+        if m == 0:
+            return np.zeros(0, dtype=_lib.PROPOSAL_DTYPE)
+        dk = self._dev(k, torch.int32)
+        out = torch.zeros((m, _lib.PROPOSAL_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mpp_sample_proposals(self.ctx, dk.data_ptr(), m, int(seed), int(offset), out.data_ptr()))
+        self.launches += 2
+        rec = out.cpu().numpy().view(_lib.PROPOSAL_DTYPE).reshape(m).copy()
+        if self.precision != "fp64":
+            snapped = snap_to_edges(np.stack([rec["add_size"], rec["add_ratio"], rec["add_angle"]], axis=1))
+            rec["add_size"], rec["add_ratio"], rec["add_angle"] = snapped[:, 0], snapped[:, 1], snapped[:, 2]
+        return rec
+
+    def proposal_probs(self, proposals: np.ndarray) -> np.ndarray:
+        """[m,2] forward / backward probabilities (Kernel.forward_probability / backward_probability)."""
+        p = np.ascontiguousarray(proposals, dtype=_lib.PROPOSAL_DTYPE)
+        m = len(p)
+        if m == 0:
+            return np.zeros((0, 2))
+        d = torch.as_tensor(p.view(np.uint8).reshape(m, -1)).to(self.device)
+        out = torch.empty((m, 2), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mpp_proposal_probs(self.ctx, d.data_ptr(), m, out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy()
+
     def sample_births(self, n: int, seed: int = 0) -> np.ndarray:
         out = torch.empty((n, 5), dtype=torch.int32, device=self.device)
         _lib.check(self.lib.mpp_sample_births(self.ctx, int(n), int(seed), out.data_ptr()))
@@ -281,6 +379,35 @@ class Engine:
         n = C.c_int()
         _lib.check(self.lib.mpp_naive_init(self.ctx, float(detection_threshold), float(nms_distance), C.byref(n)))
         return n.value
+
+    def query_neighbors(self, x: int, y: int, radius: float, euclidean: bool = False, exclude: int = _lib.NO_OBJECT,
+                        capacity: int = 1024) -> np.ndarray:
+        """Handles of PointsSet.get_potential_neighbors / get_neighbors (point_set.py:111-149)."""
+        while True:
+            out = torch.empty(max(capacity, 1), dtype=torch.int32, device=self.device)
+            n = C.c_int()
+            _lib.check(self.lib.mpp_query_neighbors(self.ctx, int(x), int(y), float(radius), int(bool(euclidean)),
+                                                    C.c_uint32(int(exclude)), capacity, out.data_ptr(), C.byref(n)))
+            self.launches += 1
+            if n.value <= capacity:
+                return out[:n.value].cpu().numpy().view(np.uint32)
+            capacity = n.value
+
+    def pair_values(self, handles_a, handles_b) -> np.ndarray:
+        """[n,2] float64 (overlap kind, alignment kind) of the given pairs; NaN where the pair does not exist."""
+        a = np.ascontiguousarray(np.asarray(handles_a, dtype=np.uint32).reshape(-1))
+        b = np.ascontiguousarray(np.asarray(handles_b, dtype=np.uint32).reshape(-1))
+        assert len(a) == len(b)
+        if len(a) == 0:
+            return np.zeros((0, 2))
+        da, db = self._dev(a.view(np.int32), torch.int32), self._dev(b.view(np.int32), torch.int32)
+        out = torch.empty((len(a), 2), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mpp_pair_values(self.ctx, da.data_ptr(), db.data_ptr(), len(a), out.data_ptr()))
+        self.launches += 1
+        return out.cpu().numpy()
+
+    def copy_state_from(self, other: "Engine"):
+        _lib.check(self.lib.mpp_copy_state(self.ctx, other.ctx))
 
     def pack_rows(self, row_lo: int, row_hi: int, capacity: int = 65536) -> torch.Tensor:
         buf = torch.empty((capacity, 8), dtype=torch.float64, device=self.device)

@@ -1,0 +1,318 @@
+"""-m gpu: the reference-facing Python API (mpp_cnn_rs_object_detection_b200.api) on the device.  The first three groups
+restate the reference's own unit tests (test/test_points_set.py, test/test_energy_graph.py,
+test/test_interacting_points_set.py) with the toy terms expressed as device terms; the rest checks the real terms against
+the golden vectors produced by the reference."""
+import numpy as np
+import pytest
+
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    import mpp_cnn_rs_object_detection_b200.api as api
+    return api
+
+
+# ------------------------------------------------------------------------------------------------ test/test_points_set.py
+def test_points_set_grid_and_membership():
+    api = _api()
+    ps = api.PointsSet(support_shape=(200, 516), maximum_interaction_radius=32)
+    assert ps._n_x == 7 and ps._n_y == 17  # test/test_points_set.py:29-41
+    pts = [api.Point(0, 0), api.Point(5, 7), api.Point(199, 515), api.Point(64, 64), api.Point(64, 64)]
+    for p in pts:
+        ps.add(p)
+    assert len(ps) == 5
+    for p in pts:
+        assert p in ps
+        assert p in ps._find_local_point_set(p)
+    assert api.Point(0, 0) not in ps  # identity, not value
+    assert set(iter(ps)) == set(pts)
+    ps.remove(pts[1])
+    assert len(ps) == 4 and pts[1] not in ps
+    with pytest.raises(KeyError):
+        ps.remove(pts[1])
+    with pytest.raises(AssertionError):
+        ps.add(api.Point(200, 0))  # out of bounds (point_set.py:99)
+    cp = ps.copy()
+    cp.remove(pts[0])
+    assert len(cp) == 3 and len(ps) == 4 and pts[0] in ps
+
+
+def test_points_set_neighbours_vs_brute_force():
+    api = _api()
+    rng = np.random.default_rng(0)
+    shape = (300, 260)
+    ps = api.PointsSet(shape, 32)
+    pts = [api.Point(int(x), int(y)) for x, y in zip(rng.integers(0, shape[0], 600), rng.integers(0, shape[1], 600))]
+    for p in pts:
+        ps.add(p)
+    for u in pts[:40]:
+        for r in (8, 32, 64):  # r=64: two cell offsets (test/test_points_set.py:222-244)
+            got = ps.get_neighbors(u, r, suppress_warnings=True)
+            want = {p for p in pts if p is not u and np.hypot(p.x - u.x, p.y - u.y) <= r}
+            assert got == want
+        pot = ps.get_potential_neighbors(u, 32)
+        for p in pot:  # Chebyshev bound of the 3x3-cell block (test/test_points_set.py:135-157)
+            assert abs(p.x // 32 - u.x // 32) <= 1 and abs(p.y // 32 - u.y // 32) <= 1
+        want_pot = {p for p in pts if p is not u and abs(p.x // 32 - u.x // 32) <= 1 and abs(p.y // 32 - u.y // 32) <= 1}
+        assert pot == want_pot
+    # churn (test/test_points_set.py:160-185)
+    alive = set(pts)
+    for k in range(2000):
+        if alive and rng.random() < 0.5:
+            p = next(iter(alive))
+            alive.remove(p)
+            ps.remove(p)
+        else:
+            p = api.Point(int(rng.integers(0, shape[0])), int(rng.integers(0, shape[1])))
+            alive.add(p)
+            ps.add(p)
+    assert len(ps) == len(alive) and set(iter(ps)) == alive
+    c = ps.random_choice(np.random.default_rng(1))
+    assert c in alive
+
+
+# ------------------------------------------------------------------------------------------------ test/test_energy_graph.py
+def _toy_graph(api):
+    eg = api.EnergyGraph(unit_energies_constructors=[api.ConstantUnitEnergy(name="unit", value=-10.0)],
+                         pair_energies_constructors=[api.DistanceIndicatorPairEnergy(name="pair", max_dist=1.0, value=1.0)])
+    ps = api.PointsSet(support_shape=(64, 64), maximum_interaction_radius=32)
+    return eg, ps
+
+
+def test_energy_graph_structure():
+    api = _api()
+    eg, ps = _toy_graph(api)
+    p1 = api.Point(10, 10)
+    ps.add(p1); eg.add_point(p1, ps)
+    assert p1 in eg.ue_per_point and len(eg.ue_per_point[p1]) == 1
+    assert p1 in eg.pe_per_point and len(eg.pe_per_point[p1]) == 0
+    p2 = api.Point(10, 11)
+    ps.add(p2); eg.add_point(p2, ps)
+    assert len(eg.ue_per_point[p2]) == 1 and len(eg.pe_per_point[p2]) == 1 and len(eg.pe_per_point[p1]) == 1
+    assert eg.pe_per_point[p2][0].point_2 is p1
+    assert eg.pe_per_point[p2][0] is eg.pe_per_point[p1][0]
+    assert eg.pe_per_point[p2][0].compute() == 1.0 and eg.ue_per_point[p2][0].compute() == -10.0
+    p3 = api.Point(20, 20)
+    ps.add(p3); eg.add_point(p3, ps)
+    assert len(eg.pe_per_point[p3]) == 0 and len(eg.pe_per_point[p2]) == 1 and len(eg.pe_per_point[p1]) == 1
+    ps.remove(p2); eg.remove_point(p2)
+    assert len(eg.pe_per_point[p3]) == 0 and len(eg.pe_per_point[p1]) == 0
+    assert p2 not in eg.pe_per_point
+
+
+def test_energy_graph_compute_delta_known_answers():
+    """test/test_energy_graph.py:177-244: -10, -8, -10, +1, -10, -8, 0, +7."""
+    api = _api()
+    eg, ps = _toy_graph(api)
+    P, B, D, T = api.Perturbation, api.BirthKernel, api.DeathKernel, api.DataDrivenTranslationKernel
+    want = gu.known_answers()["energy_graph_compute_delta"]
+    got = []
+
+    def add(p):
+        ps.add(p); eg.add_point(p, ps)
+
+    p1 = api.Point(10, 10)
+    got.append(eg.compute_delta(ps, P(type=B, removal=None, addition=p1))); add(p1)
+    p2 = api.Point(10, 11)
+    got.append(eg.compute_delta(ps, P(type=B, removal=None, addition=p2))); add(p2)
+    p3 = api.Point(20, 20)
+    got.append(eg.compute_delta(ps, P(type=B, removal=None, addition=p3))); add(p3)
+    p32 = api.Point(10, 12)
+    got.append(eg.compute_delta(ps, P(type=T, removal=p3, addition=p32)))
+    ps.remove(p3); eg.remove_point(p3); add(p32)
+    p4 = api.Point(5, 5)
+    got.append(eg.compute_delta(ps, P(type=B, removal=None, addition=p4))); add(p4)
+    p5 = api.Point(5, 6)
+    got.append(eg.compute_delta(ps, P(type=B, removal=None, addition=p5))); add(p4)
+    p6 = api.Point(5, 7)
+    add(p6)
+    p61 = api.Point(5, 8)
+    got.append(eg.compute_delta(ps, P(type=T, removal=p6, addition=p61)))
+    ps.remove(p6); eg.remove_point(p6); add(p61)
+    got.append(eg.compute_delta(ps, P(type=D, removal=p2, addition=None)))
+    assert got == want
+    # total energy / subsets (test/test_energy_graph.py:94-174)
+    total = eg.total_energy(ps)
+    vec = eg.compute_subset(list(ps), return_vector=True)
+    assert set(vec) == {"unit", "pair"} and total == sum(vec["unit"]) + sum(vec["pair"])
+
+
+# ------------------------------------------------------------------------------------------------ test/test_interacting_points_set.py
+def _toy_eps(api, pts, shape=(10, 10)):
+    return api.EPointsSet(points=pts, support_shape=shape, unit_energies_constructors=[api.ConstantUnitEnergy(name="ue", value=1.0)],
+                          pair_energies_constructors=[api.DistanceIndicatorPairEnergy(name="pe", max_dist=3, value=1.0, strict=True)])
+
+
+def test_epointsset_known_answers():
+    api = _api()
+    ka = gu.known_answers()
+    pts = [api.Point(0, 0), api.Point(0, 1), api.Point(0, 4)]
+    s = _toy_eps(api, pts)
+    e = [s.total_energy()]
+    s.add(api.Point(0, 5))
+    e.append(s.total_energy())
+    e.append(_toy_eps(api, [api.Point(0, 0), api.Point(0, 1), api.Point(1, 0)]).total_energy())
+    assert e == ka["epointsset_total_energy"]  # 5, 8, 6 (test/test_interacting_points_set.py:149-208)
+    some = [api.Point(0, 0), api.Point(0, 1), api.Point(0, 5)]
+    p0 = _toy_eps(api, some)
+    pert1 = api.Perturbation(type=api.DeathKernel, removal=some[2])
+    e0 = p0.total_energy()
+    d1 = p0.energy_delta(pert1)
+    p1 = p0.apply_perturbation(pert1)
+    assert e0 == 5.0 and p1.total_energy() == e0 + d1 and len(p0) == 3 and len(p1) == 2
+    pert2 = api.Perturbation(type=api.DataDrivenTranslationKernel, removal=some[2], addition=api.Point(1, 0))
+    d2 = p0.energy_delta(pert2)
+    p2 = p0.apply_perturbation(pert2)
+    assert [d1, d2] == ka["epointsset_energy_delta"] and p2.total_energy() == e0 + d2 == 6.0
+    back = p2.unapply_perturbation(pert2)
+    assert back.total_energy() == e0 and some[2] in back
+    # membership / iteration / errors (test/test_interacting_points_set.py:46-140, energy_point_set.py:88-116)
+    for p in some:
+        assert p in p0 and p in p0.points and p in p0.energy_graph.ue_per_point and p in p0.energy_graph.pe_per_point
+    with pytest.raises(KeyError):
+        p0.energy_delta(api.Perturbation(type=api.DeathKernel, removal=api.Point(3, 3)))
+    with pytest.raises(ValueError):
+        p0.papangelou(some[0])
+    assert p0.papangelou(some[2], remove_u_from_point_set=True, return_energy_delta=True) == -d1
+    with pytest.raises(AssertionError):
+        api.EPointsSet([], (10, 10), [api.ConstantUnitEnergy(name="a", value=1.0), api.ConstantUnitEnergy(name="a", value=2.0)], [])
+
+
+def test_python_plugin_terms_are_rejected_loudly():
+    api = _api()
+
+    class MyUnit(api.UnitEnergyConstructor):
+        def compute(self, u):
+            return 1.0
+
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        api.EPointsSet([], (10, 10), [MyUnit(name="mine")], [])
+
+
+# ------------------------------------------------------------------------------------------------ real terms vs golden
+def _image(api, det, marks, name="img"):
+    return api.ImageWMaps(name=name, shape=det.shape, image=None, detection_map=det, param_dist_maps=list(marks),
+                          mappings=api.default_mappings(), param_names=["size", "ratio", "angle"])
+
+
+def _setup(api, cfg):
+    if cfg == "legacy":
+        c = gu.CALIB_HRCM
+        s = api.LegacyEnergySetup(calibration_params={}, energy_calibration=api.LegacyEnergiesCalibration(
+            c["detection_threshold"], list(c["coefs"]), list(c["intercepts"]), c["min_area"], c["max_area"]))
+        h = gu.HRC
+        comb = api.HierarchicalEnergyCombinator(np.array(h["weights_data"]), np.array(h["weights_prior"]), np.array(h["data_prior_weights"]),
+                                                h["detection_threshold"], h["bias"])
+    else:
+        c = gu.CALIB_LOG
+        s = api.NoCalibrationEnergySetup(ratio_prior=True)
+        s.energy_calibration = api.NoCalibEnergiesCalibration(c["min_area"], c["max_area"])
+        comb = api.LogisticEnergyCombinator(weights=gu.LOG_WEIGHTS, bias=gu.LOG_BIAS, energy_names=s.energy_names)
+    return s, comb
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_epointsset_real_terms_match_reference(cfg):
+    api = _api()
+    g = gu.load(f"energies_{cfg}.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, cfg)
+    unit, pair = setup.make_energies(_image(api, det, marks))
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    eps = api.EPointsSet(rects, det.shape, unit, pair)
+    vec = eps.energy_graph.compute_subset(rects, return_vector=True)
+    names = [str(s) for s in g["names"]]
+    assert set(vec) == set(names)
+    got = np.array([vec[k] for k in names]).T
+    np.testing.assert_allclose(got, g["vectors"], rtol=1e-5, atol=1e-5)
+    assert abs(eps.energy_graph.compute_subset(rects, energy_combinator=comb) - float(g["comb_total"])) < 1e-3
+    assert abs(eps.total_energy() - float(g["raw_total"])) < 2e-3
+    # the combinator's own compute() (device) on the reference's vectors
+    assert abs(comb.compute({k: list(g["vectors"][:, i]) for i, k in enumerate(names)}) - float(g["comb_total"])) < 1e-9 * max(1, abs(float(g["comb_total"])))
+    for k, (ri, add) in enumerate(zip(g["pert_removal"], g["pert_addition"])):
+        rem = rects[ri] if ri >= 0 else None
+        a = None if np.isnan(add[0]) else api.Rectangle(int(add[0]), int(add[1]), add[2], add[3], add[4])
+        p = api.Perturbation(type=api.BirthKernel, removal=rem, addition=a)
+        assert abs(eps.energy_delta(p, energy_combinator=comb) - g["delta_comb"][k]) < 2e-5 + 1e-5 * abs(g["delta_comb"][k])
+        assert abs(eps.energy_delta(p) - g["delta_raw"][k]) < 4e-5 + 1e-5 * abs(g["delta_raw"][k])
+    assert len(eps) == len(rects)
+    # batched Papangelou scores == one by one (mpp_model.py:296-304)
+    objs, scores = eps.papangelou_all(energy_combinator=comb)
+    one = [eps.papangelou(u, energy_combinator=comb, remove_u_from_point_set=True) for u in objs[:5]]
+    np.testing.assert_allclose(scores[:5], one, rtol=1e-6)
+    # naive initial configuration (sample_rjmcmc.py:23-35)
+    naive = api.naive_detection(_image(api, det, marks), float(g["naive_threshold"]), energy_setup=setup)
+    got_n = np.array(sorted((r.x, r.y, r.size, r.ratio, r.angle) for r in naive))
+    want_n = np.array(sorted(tuple(r) for r in g["naive"]))
+    np.testing.assert_allclose(got_n, want_n, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_kernel_probabilities_match_reference(cfg):
+    """Kernel.forward_probability / backward_probability through the API on the reference's recorded proposals."""
+    api = _api()
+    g = gu.load(f"energies_{cfg}.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, cfg)
+    img = _image(api, det, marks)
+    unit, pair = setup.make_energies(img)
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    eps = api.EPointsSet(rects, det.shape, unit, pair)
+    kernels, p = api.make_kernels(img, intensity=float(g["intensity"]), rng=np.random.default_rng(0))
+    np.testing.assert_allclose(p, g["p_kernels"], rtol=0, atol=1e-15)
+    for row in g["kernel_probs"]:
+        kid, ri = int(row[0]), int(row[1])
+        add = None if np.isnan(row[2]) else api.Rectangle(int(row[2]), int(row[3]), row[4], row[5], row[6])
+        data = {"delta": np.array([row[7], row[8]]) if kid == 4 else float(row[7]), "param_id": int(row[9]), "new_param_class_value": int(row[10])}
+        u = api.Perturbation(type=kernels[kid].__class__, removal=rects[ri] if ri >= 0 else None, addition=add, data=data)
+        f, b = kernels[kid].forward_probability(eps.points, u), kernels[kid].backward_probability(eps.points, u)
+        assert abs(f - row[11]) <= 3e-6 * abs(row[11]) + 1e-300, (kid, f, row[11])
+        assert abs(b - row[12]) <= 3e-6 * abs(row[12]) + 1e-300, (kid, b, row[12])
+
+
+def test_rjmcmc_step_and_run_and_sample_rjmcmc():
+    api = _api()
+    g = gu.load("energies_legacy.npz")
+    truth, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, "legacy")
+    img = _image(api, det, marks)
+    unit, pair = setup.make_energies(img)
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    # (1) step-by-step through the Kernel objects
+    eps = api.EPointsSet(rects, det.shape, unit, pair)
+    kernels, p = api.make_kernels(img, intensity=max(1, len(rects)), rng=np.random.default_rng(0))
+    chain = api.RJMCMC(t0=0.05, kernels=kernels, p_kernels=p, initial_state=eps, stopping_condition=api.StopOnMaxIter(59),
+                       rng=np.random.default_rng(3), energy_combinator=comb, alpha_t=1.0)
+    n_acc = 0
+    for _ in range(60):
+        s = chain.step()
+        n_acc += bool(s.move_accepted)
+        assert s.n_points == len(eps)
+    with pytest.raises(StopIteration):
+        chain.step()
+    assert 0 < n_acc < 60
+    # every stored object is consistent with the device (energies still evaluate)
+    vec = eps.energy_graph.compute_subset(list(eps), return_vector=True)
+    assert len(vec["PositionEnergy"]) == len(eps)
+    # (2) whole chain on the device
+    eps2 = api.EPointsSet(rects, det.shape, unit, pair)
+    chain2 = api.RJMCMC(t0=0.05, kernels=kernels, p_kernels=p, initial_state=eps2, stopping_condition=api.StopOnMaxIter(2000),
+                        rng=np.random.default_rng(4), energy_combinator=comb, alpha_t=0.999,
+                        sampling_rule=lambda step: step >= 1000 and step % 500 == 0)
+    states, summaries = chain2.run()
+    assert len(summaries) == 2002 and summaries[-1].iter == 2000  # max_iter + 1 steps (stopping.py:42)
+    assert len(states) == 1 + 3  # snapshots at 1000, 1500, 2000
+    assert abs(len(states[-1]) - len(rects)) < 0.5 * len(rects)
+    # (3) the drop-in entry point, both samplers
+    for sampler in ("parallel", "sequential"):
+        out = api.sample_rjmcmc(image_data=img, rng=np.random.default_rng(5), num_samples=1, energy_combinator=comb, init_config="naive",
+                                init_temperature=1.0, alpha_t=0.999, burn_in=4000, energy_setup=setup, samples_interval=64,
+                                target_temperature=0.0, sampler=sampler)
+        assert len(out) == 1
+        final = list(out[0])
+        assert all(isinstance(r, api.Rectangle) for r in final)
+        # annealed to T ~ 0.02: the configuration is close to the objects the maps were synthesised from
+        assert 0.5 * len(truth) <= len(final) <= 1.6 * len(truth), (sampler, len(final), len(truth))
