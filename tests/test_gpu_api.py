@@ -309,10 +309,10 @@ def test_rjmcmc_step_and_run_and_sample_rjmcmc():
     # (3) the drop-in entry point, both samplers
     for sampler in ("parallel", "sequential"):
         out = api.sample_rjmcmc(image_data=img, rng=np.random.default_rng(5), num_samples=1, energy_combinator=comb, init_config="naive",
-                                init_temperature=1.0, alpha_t=0.999, burn_in=4000, energy_setup=setup, samples_interval=64,
+                                init_temperature=0.1, alpha_t=0.9995, burn_in=6000, energy_setup=setup, samples_interval=64,
                                 target_temperature=0.0, sampler=sampler)
         assert len(out) == 1
         final = list(out[0])
         assert all(isinstance(r, api.Rectangle) for r in final)
-        # annealed to T ~ 0.02: the configuration is close to the objects the maps were synthesised from
+        # annealed from T=0.1 to ~0.005 (a T0=1 schedule needs the full 30k-step budget): the configuration is close to the objects the maps were synthesised from
         assert 0.5 * len(truth) <= len(final) <= 1.6 * len(truth), (sampler, len(final), len(truth))
