@@ -202,7 +202,7 @@ int mpp_replay(mpp_ctx *ctx, const mpp_proposal *props, int m, double t0, double
 /* Device-resident sequential chain: RJMCMC.run (rjmcmc.py:83-181) with the reference's eight global kernels
  * (make_kernels.py:88-144: uniform pick among all objects point_set.py:176-185, global births, Lambda = intensity)
  * and Philox4x32-10 in place of the numpy Generator.  One proposal at a time, strictly in order, on one warp.
- * trace (device, n_steps entries) may be NULL; counters_host[4] as in mpp_run_sweeps (may be NULL). */
+ * trace (device, n_steps entries) may be NULL; counters_host[8] as in mpp_run_sweeps (may be NULL). */
 int mpp_run_chain(mpp_ctx *ctx, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed,
                   uint64_t step_offset, mpp_step_result *trace, unsigned long long *counters_host);
 
@@ -223,10 +223,22 @@ int mpp_combine(const mpp_model_params *model_host, const double *vectors, int n
 /* Parallel sampler (new; replaces the sequential loop RJMCMC.run rjmcmc.py:172-181).  Each sweep visits the
  * `stride`^2 colour classes of the cell grid once; every active cell performs `proposals_per_visit` local
  * Metropolis-Hastings-Green proposals with Philox4x32-10 randomness keyed by (seed, cell, sweep).  Temperature
- * is multiplied by alpha_t once per *sweep*.  counters_host[4] (may be NULL) receives
- * {proposals, accepted, births accepted, deaths accepted} and synchronises. */
+ * is multiplied by alpha_t once per *sweep*.  counters_host[8] (may be NULL) receives
+ * {proposals, accepted, births accepted, deaths accepted, proposals whose Delta-energy was evaluated, 0, 0, 0} and
+ * synchronises. */
 int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stride, double t0, double alpha_t,
                    double t_target, uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host);
+
+/* Parallel sampler, second generation (the production path).  Sampling windows are the 32-px grid cells shifted by a
+ * per-sweep pseudo-random offset, coloured 3x3; one CTA per window stages everything within 64 px of its window in
+ * shared memory once and runs `proposals_per_visit` (<= 64) proposals from there; its `n_warps` (1, 2, 4, 8) warps
+ * evaluate consecutive proposals speculatively (the chain does not depend on n_warps).  The kernel mixture is the
+ * reference's when a window holds objects and births-only when it is empty.  debug_maxdiff (device float, may be
+ * NULL): every Delta-energy is also recomputed by brute force and the largest |difference| is written there.
+ * counters_host as in mpp_run_sweeps. */
+int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, double t0, double alpha_t,
+                    double t_target, uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host,
+                    float *debug_maxdiff);
 
 /* Draws n pixels from the normalised detection map (sample_point_2d, utils/sampler2d.py:39-46, as used by
  * RectangleSampler.sample shape_samplers.py:90-94) and their three mark classes (shape_samplers.py:113-117):

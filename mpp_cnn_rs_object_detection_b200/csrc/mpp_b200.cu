@@ -12,6 +12,7 @@
 #include "mpp_device.cuh"
 #include "mpp_proposals.cuh"
 #include "mpp_chain.cuh"
+#include "mpp_sweep2.cuh"
 
 // ================================================================================================ host ctx
 struct mpp_ctx {
@@ -22,6 +23,7 @@ struct mpp_ctx {
     uint32_t *d_mask = nullptr;
     void *d_recs = nullptr;
     double *d_cell_cdf = nullptr;
+    double *d_rowcum = nullptr;         // [H][W+1] row prefix sums of det
     int *d_scan = nullptr;              // [ncell + 1] exclusive prefix of per-cell populations
     int *d_nobj = nullptr;
     int *d_rowcount = nullptr;          // [nx] objects per row of cells (global uniform pick)
@@ -36,6 +38,7 @@ struct mpp_ctx {
     ModelDev m;
     KernDev k;
     int *h_pinned = nullptr;            // small pinned read-back area (16 x 8 bytes)
+    uint32_t window_uid_next = 0x80000000u;  // uids of objects born in mpp_run_windows: host-tracked, upper half of the uid space
 };
 
 static thread_local std::string g_last_error;
@@ -56,6 +59,7 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.recs = reinterpret_cast<Rec<R> *>(h->d_recs);
     c.det = h->det; c.marks = h->marks; c.det_sum = h->det_sum;
     c.cell_cdf = h->d_cell_cdf;
+    c.rowcum = h->d_rowcum;
     c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
     c.m = h->m; c.k = h->k;
     return c;
@@ -94,6 +98,22 @@ __global__ void k_cell_mass(const float *__restrict__ det, int H, int W, int ny,
     }
     s = warp_sum(s);
     if (lane == 0) mass[cell] = s;
+}
+
+// K5b: exclusive prefix sums of every row of det (warp per row)
+__global__ void k_row_prefix(const float *__restrict__ det, int H, int W, double *__restrict__ rowcum) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= H) return;
+    const float *src = det + (size_t)row * W;
+    double *dst = rowcum + (size_t)row * ((size_t)W + 1);
+    double base = 0.0;
+    if (lane == 0) dst[0] = 0.0;
+    for (int b = 0; b < W; b += 32) {
+        const double v = (b + lane < W) ? (double)__ldg(src + b + lane) : 0.0;
+        const double incl = warp_incl_scan(v, lane);
+        if (b + lane < W) dst[b + lane + 1] = base + incl;
+        base += __shfl_sync(MPP_FULL, incl, 31);
+    }
 }
 
 // single-block inclusive scan of doubles in place (ncell <= a few 1e5)
@@ -427,6 +447,7 @@ __global__ void k_run_chain(Ctx<R> c, int *__restrict__ row_count, int n_steps, 
         atomicAdd(c.counters + 1, (unsigned long long)n_acc);
         atomicAdd(c.counters + 2, (unsigned long long)n_birth);
         atomicAdd(c.counters + 3, (unsigned long long)n_death);
+        atomicAdd(c.counters + 4, (unsigned long long)n_steps);
     }
 }
 
@@ -481,7 +502,7 @@ __global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj
     const double cell_mass = c.cell_cdf[cell] - (cell > 0 ? c.cell_cdf[cell - 1] : 0.0);
     const double q_data = cell_mass / c.cell_cdf[c.ncell - 1];
     Philox rng(seed, (uint32_t)cell, (uint32_t)sweep_id, (uint32_t)(sweep_id >> 32));
-    unsigned n_acc = 0, n_birth = 0, n_death = 0;
+    unsigned n_acc = 0, n_birth = 0, n_death = 0, n_eval = 0;
     int dn = 0;
     double cdf[8];
     { double acc = 0; for (int k = 0; k < 8; ++k) { acc += c.k.p[k]; cdf[k] = acc; } }
@@ -588,6 +609,7 @@ __global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj
             if (dm == 0xffffffffu) valid = false;
         }
         if (valid && (has_rem || has_add)) {
+            ++n_eval;
             const R d = warp_delta(c, s, has_rem, rh, rem, has_add, add, lane);
             double fwd, bwd;
             proposal_probs(c, kernel, has_rem, rem, has_add, add, d0, d1, param_id, new_class, (double)nc, lambda, lane, &fwd, &bwd);
@@ -613,6 +635,7 @@ __global__ void k_sweep(Ctx<R> c, int stride, int ci, int cj, int n_ai, int n_aj
         atomicAdd(c.counters + 1, (unsigned long long)n_acc);
         atomicAdd(c.counters + 2, (unsigned long long)n_birth);
         atomicAdd(c.counters + 3, (unsigned long long)n_death);
+        atomicAdd(c.counters + 4, (unsigned long long)n_eval);
         if (dn) atomicAdd(c.n_objects, dn);
     }
 }
@@ -824,19 +847,20 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_mask, sizeof(uint32_t) * h->ncell));
     CUDA_TRY(cudaMalloc(&h->d_recs, rec * (size_t)h->ncell * MPP_CELL_CAPACITY));
     CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * h->ncell));
+    CUDA_TRY(cudaMalloc(&h->d_rowcum, sizeof(double) * (size_t)height * ((size_t)width + 1)));
     CUDA_TRY(cudaMalloc(&h->d_scan, sizeof(int) * (h->ncell + 1)));
     CUDA_TRY(cudaMalloc(&h->d_nobj, sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->d_rowcount, sizeof(int) * h->nx));
     CUDA_TRY(cudaMalloc(&h->d_next_uid, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 4));
+    CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, 128));
     CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_recs, 0, rec * (size_t)h->ncell * MPP_CELL_CAPACITY, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_next_uid, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
     memset(&h->m, 0, sizeof(h->m));
     memset(&h->k, 0, sizeof(h->k));
     // dynamic shared memory opt-in for the warp-scratch kernels
@@ -858,7 +882,7 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     if (!h) return MPP_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_scan); cudaFree(h->d_nobj);
+    cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
     cudaFree(h->d_rowcount); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
@@ -872,6 +896,7 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
     const int blocks = (h->ncell + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     k_cell_mass<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->ny, h->ncell, h->d_cell_cdf);
     k_scan_double<<<1, 1024, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
+    k_row_prefix<<<(h->H + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->d_rowcum);
     CUDA_TRY(cudaGetLastError());
     if (det_sum > 0.0) {
         h->det_sum = (float)det_sum;
@@ -1104,10 +1129,10 @@ int mpp_run_sweeps(mpp_ctx *h, int n_sweeps, int per_visit, int stride, double t
     CUDA_TRY(cudaGetLastError());
     if (counters_host) {
         unsigned long long *tmp = reinterpret_cast<unsigned long long *>(h->h_pinned);
-        CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        for (int i = 0; i < 4; ++i) counters_host[i] = tmp[i];
+        for (int i = 0; i < 8; ++i) counters_host[i] = tmp[i];
         return check_device_errors(h);
     }
     return MPP_OK;
@@ -1143,7 +1168,7 @@ int mpp_naive_init(mpp_ctx *h, double detection_threshold, double nms_distance, 
         if (!h->h_pinned[1]) break;
         if (!h->h_pinned[0]) return fail(MPP_ERR_CUDA, "mpp_naive_init: NMS did not progress");
     }
-    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
     DISPATCH(h, (k_nms_insert<R><<<blocks, 256, 0, h->stream>>>(device_view<R>(h), h->d_nms_state)));
     CUDA_TRY(cudaGetLastError());
     int rc = check_device_errors(h);
@@ -1189,11 +1214,71 @@ static int refresh_row_counts(mpp_ctx *h) {
 
 static int read_counters(mpp_ctx *h, unsigned long long *counters_host) {
     unsigned long long *tmp = reinterpret_cast<unsigned long long *>(h->h_pinned);
-    CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 4, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 4; ++i) counters_host[i] = tmp[i];
+    for (int i = 0; i < 8; ++i) counters_host[i] = tmp[i];
     return check_device_errors(h);
+}
+
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <typename R, int NW>
+static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp, uint64_t seed,
+                                 uint64_t sweep_id, float *dbg) {
+    const uint32_t uid_base = h->window_uid_next;
+    h->window_uid_next += (uint32_t)(n_wi * n_wj * per_visit);
+    if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;  // wrapped: stay in the upper half
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32) * sizeof(R);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_sweep2<R, NW><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id, uid_base, dbg);
+    return cudaGetLastError();
+}
+
+extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_warps, double t0, double alpha_t, double t_target,
+                               uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host, float *debug_maxdiff) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_windows: set maps, model and kernels first");
+    if (n_sweeps < 0 || per_visit < 1 || per_visit > 64 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 64)");
+    if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 1, 2, 4 or 8");
+    if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double temp = t0;
+    for (int s = 0; s < n_sweeps; ++s) {
+        const uint64_t sweep_id = sweep_offset + (uint64_t)s;
+        const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
+        const int ox = (int)(hsh & 31), oy = (int)((hsh >> 5) & 31);
+        const int nwx = (h->H + ox + 31) / 32, nwy = (h->W + oy + 31) / 32;
+        for (int ci = 0; ci < 3; ++ci)
+            for (int cj = 0; cj < 3; ++cj) {
+                const int n_wi = ci < nwx ? (nwx - ci + 2) / 3 : 0, n_wj = cj < nwy ? (nwy - cj + 2) / 3 : 0;
+                if (n_wi * n_wj == 0) continue;
+                cudaError_t e;
+#define MPP_LAUNCH_W(NWV) (h->precision == MPP_PRECISION_FP64 \
+        ? launch_sweep2<double, NWV>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff) \
+        : launch_sweep2<float, NWV>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff))
+                switch (n_warps) {
+                case 1: e = MPP_LAUNCH_W(1); break;
+                case 2: e = MPP_LAUNCH_W(2); break;
+                case 4: e = MPP_LAUNCH_W(4); break;
+                default: e = MPP_LAUNCH_W(8); break;
+                }
+#undef MPP_LAUNCH_W
+                if (e != cudaSuccess) return fail(MPP_ERR_CUDA, std::string("k_sweep2 launch: ") + cudaGetErrorString(e));
+            }
+        if (temp > t_target) temp *= alpha_t;
+    }
+    if (counters_host) return read_counters(h, counters_host);
+    return MPP_OK;
 }
 
 extern "C" int mpp_run_chain(mpp_ctx *h, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed, uint64_t step_offset,

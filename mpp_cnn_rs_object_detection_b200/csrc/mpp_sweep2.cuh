@@ -1,0 +1,670 @@
+// K6 v2: parallel colour-sweep sampler with shared-memory resident windows.
+//
+// One CTA owns one 32x32-px sampling window for the whole visit.  The objects within 64 px of the window are staged
+// ONCE in shared memory (geometry, unit energies, and for every object that a move in the window can affect its
+// top-2 partner reductions), then `per_visit` Metropolis-Hastings-Green proposals run from shared memory; only the
+// map gathers of a proposed object touch L2/HBM.  The NW warps of the CTA evaluate NW consecutive proposals of the
+// chain speculatively against the same state; the first accepted one is committed and the later ones are discarded and
+// re-drawn from their own Philox counters, so the chain is bit-identical for every NW ("speculative moves").
+//
+// Windows are the cells of the 32-px grid shifted by a per-sweep random offset (ox, oy), coloured 3x3: windows of one
+// colour are >= 65 px apart (> the 64-px reach of a Delta-energy), so they commute.  Moves that leave the window are
+// rejected (symmetric restriction); the random shift lets objects cross every boundary over time.
+// Reference rows: R15-R21 (rjmcmc.py:83-164, kernels/*.py); energies as in mpp_device.cuh.
+#pragma once
+#include "mpp_chain.cuh"
+
+#define W2_K 96          // staged objects per window (window +- 64 px)
+#define W2_MAXW 8        // warps per window (speculation depth)
+#define W2_EPS 1e-16f
+
+enum : unsigned char { W2_ALIVE = 1, W2_WIN = 2, W2_INNER = 4 };
+
+template <typename R>
+struct WinState {
+    int n;        // staged entries (alive or free)
+    int n_win;    // alive objects inside the window
+    int x0, x1, y0, y1;   // window pixel box (clipped to the image)
+    int cx0, cy0;         // first storage cell (row, col) of the 2x2 block the window overlaps
+    uint32_t cmask[4];    // private copy of the occupancy masks of those storage cells (NO cell: 0xffffffff)
+    int ccell[4];         // their linear indices (-1: outside the grid)
+    uint32_t uid_base;
+    int dn, n_acc, n_birth, n_death, n_eval, n_done;
+    float row_mass[32];   // detection mass of each window row;  win_mass = their sum
+    double win_mass;
+    int x[W2_K], y[W2_K];
+    uint32_t cls[W2_K], handle[W2_K], uid[W2_K];
+    R size[W2_K], ratio[W2_K], angle[W2_K];
+    R hl[W2_K], hw[W2_K], ca[W2_K], sa[W2_K];
+    R pos[W2_K], tm0[W2_K], tm1[W2_K], tm2[W2_K];      // unit data terms as the combinator sees them
+    R dm0[W2_K], dm1[W2_K], dm2[W2_K];                  // per-mark energies (window objects; legacy: before the mean)
+    float detv[W2_K], pn0[W2_K], pn1[W2_K], pn2[W2_K];  // det value and normalised mark probabilities (window objects)
+    R ov1[W2_K], ov2[W2_K], al1[W2_K], al2[W2_K];
+    short aov[W2_K], aal[W2_K];
+    unsigned char flags[W2_K];
+    uint32_t order[W2_K];  // staging scratch: handles in canonical order
+    // speculation results, one slot per warp
+    int res_accept[W2_MAXW], res_eval[W2_MAXW];
+};
+
+template <typename R>
+struct Cand {  // the object a proposal wants to add (warp-uniform registers)
+    int x, y;
+    uint32_t cls;
+    R size, ratio, angle, hl, hw, ca, sa;
+    R pos, dm0, dm1, dm2;
+    float detv, pn0, pn1, pn2;
+};
+
+template <typename R>
+__device__ __forceinline__ void shape_terms(const ModelDev &m, R dm0, R dm1, R dm2, R *t0, R *t1, R *t2) {
+    if (m.setup == MPP_SETUP_LEGACY) {  // float(np.mean([d0,d1,d2])) data_energies.py:43
+        *t0 = (R)__fdiv_rn(__fadd_rn(__fadd_rn((float)dm0, (float)dm1), (float)dm2), 3.0f);
+        *t1 = 0; *t2 = 0;
+    } else {
+        *t0 = dm0; *t1 = dm1; *t2 = dm2;
+    }
+}
+
+__device__ __forceinline__ float mark_energy_f32(const ModelDev &m, int i, float p) {
+    if (m.setup == MPP_SETUP_LEGACY) return m.premapped ? p : legacy_remap_f32(p, m.coef[i], m.icpt[i]);
+    return m.premapped ? p : -p;
+}
+
+// det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): one coalesced
+// 128-byte row per mark (lane = class) + one 4-byte gather, all independent -> a single memory round trip.
+template <typename R>
+__device__ __forceinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
+    const float v0 = __ldg(mark_row(c, 0, x, y) + lane), v1 = __ldg(mark_row(c, 1, x, y) + lane), v2 = __ldg(mark_row(c, 2, x, y) + lane);
+    const float d = __ldg(c.det + (size_t)x * c.W + y);
+    const float s0 = warp_sum(v0), s1 = warp_sum(v1), s2 = warp_sum(v2);
+    const float p0 = __shfl_sync(MPP_FULL, v0, cls_of(cls, 0)), p1 = __shfl_sync(MPP_FULL, v1, cls_of(cls, 1)),
+                p2 = __shfl_sync(MPP_FULL, v2, cls_of(cls, 2));
+    *detv = d;
+    pn[0] = p0 / s0; pn[1] = p1 / s1; pn[2] = p2 / s2;
+    dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
+}
+
+// RectangleSampler.get_point_density (shape_samplers.py:103-108) from staged factors
+template <typename R>
+__device__ __forceinline__ float dens_of(const Ctx<R> &c, float detv, float pn0, float pn1, float pn2) {
+    return (detv / c.det_sum) * (pn0 * pn1 * pn2) * ((float)c.H * (float)c.W * 32768.0f);
+}
+
+template <typename R>
+__device__ __forceinline__ Geo<R> geo_w(const WinState<R> &w, int k) {
+    Geo<R> g; g.x = w.x[k]; g.y = w.y[k]; g.hl = w.hl[k]; g.hw = w.hw[k]; g.ca = w.ca[k]; g.sa = w.sa[k];
+    return g;
+}
+
+// top-2 partner reductions of staged entry k over every other alive staged entry (one lane, serial loop)
+template <typename R>
+__device__ void recompute_top2(const ModelDev &m, WinState<R> &w, int k, R *sx, R *sy) {
+    R o1 = 0, o2 = 0, a1 = 0, a2 = 0;
+    int ao = -1, aa = -1;
+    const Geo<R> gk = geo_w(w, k);
+    const int n = w.n;
+    for (int v = 0; v < n; ++v) {
+        if (v == k || !(w.flags[v] & W2_ALIVE)) continue;
+        const int dx = w.x[v] - gk.x, dy = w.y[v] - gk.y, d2 = dx * dx + dy * dy;
+        if (d2 > m.max_d2) continue;
+        const Geo<R> gv = geo_w(w, v);
+        if (d2 <= m.ov_d2) {
+            const R o = pair_overlap(m, gk, gv, d2, sx, sy);
+            if (o > o1) { o2 = o1; o1 = o; ao = v; } else if (o > o2) o2 = o;
+        }
+        if (d2 <= m.al_d2) {
+            const R a = align_magnitude(gk, gv, m.rewarding);
+            if (a > a1) { a2 = a1; a1 = a; aa = v; } else if (a > a2) a2 = a;
+        }
+    }
+    w.ov1[k] = o1; w.ov2[k] = o2; w.al1[k] = a1; w.al2[k] = a2; w.aov[k] = (short)ao; w.aal[k] = (short)aa;
+}
+
+template <typename R>
+__device__ __forceinline__ R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
+    Terms<R> t;
+    t.pos = w.pos[k]; t.m0 = w.tm0[k]; t.m1 = w.tm1[k]; t.m2 = w.tm2[k];
+    t.ov = ov; t.al = (m.rewarding ? (R)-1 : (R)1) * al;
+    t.area = area_prior<R>(m, w.hl[k], w.hw[k]);
+    t.ratio = r_abs((R)m.target_ratio - w.ratio[k]);
+    return combine(m, t);
+}
+
+// Delta-energy of removing staged entry r (r < 0: none) and/or adding `a` (has_add), from the staged state only.
+template <typename R>
+__device__ R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy) {
+    Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
+    R acc = 0, ov_add = 0, al_add = 0;
+    const int n = w.n;
+    for (int k = lane; k < n; k += 32) {
+        if (k == r || !(w.flags[k] & W2_ALIVE)) continue;
+        bool touched = false;
+        R ov_b = w.ov1[k], al_b = w.al1[k], ov_a = ov_b, al_a = al_b;
+        if (r >= 0) {
+            const int dx = w.x[k] - rx, dy = w.y[k] - ry;
+            if (dx * dx + dy * dy <= m.max_d2) {
+                touched = true;
+                if (w.aov[k] == r) ov_a = w.ov2[k];
+                if (w.aal[k] == r) al_a = w.al2[k];
+            }
+        }
+        if (has_add) {
+            const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
+            if (d2 <= m.max_d2) {
+                touched = true;
+                const Geo<R> gk = geo_w(w, k);
+                if (d2 <= m.ov_d2) { const R o = pair_overlap(m, gk, ga, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
+                if (d2 <= m.al_d2) { const R al = align_magnitude(gk, ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
+            }
+        }
+        if (touched) acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, ov_b, al_b);
+    }
+    acc = warp_sum(acc);
+    if (has_add) {
+        ov_add = warp_max(ov_add); al_add = warp_max(al_add);
+        Terms<R> t;
+        t.pos = a.pos;
+        shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
+        t.ov = ov_add; t.al = (m.rewarding ? (R)-1 : (R)1) * al_add;
+        t.area = area_prior<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.target_ratio - a.ratio);
+        acc += combine(m, t);
+    }
+    if (r >= 0) acc -= f_obj(m, w, r, w.ov1[r], w.al1[r]);
+    return acc;
+}
+
+// brute-force version of delta_staged (debug): recomputes every reduction without the top-2 machinery
+template <typename R>
+__device__ R delta_brute(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy) {
+    Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    R acc = 0;
+    const int n = w.n;
+    for (int k = lane; k < n; k += 32) {
+        if (!(w.flags[k] & W2_ALIVE)) continue;
+        R ob = 0, ab = 0, oa = 0, aa = 0;
+        const Geo<R> gk = geo_w(w, k);
+        for (int v = 0; v < n; ++v) {
+            if (v == k || !(w.flags[v] & W2_ALIVE)) continue;
+            const int dx = w.x[v] - gk.x, dy = w.y[v] - gk.y, d2 = dx * dx + dy * dy;
+            if (d2 > m.max_d2) continue;
+            const Geo<R> gv = geo_w(w, v);
+            R o = 0, al = 0;
+            if (d2 <= m.ov_d2) o = pair_overlap(m, gk, gv, d2, sx, sy);
+            if (d2 <= m.al_d2) al = align_magnitude(gk, gv, m.rewarding);
+            ob = r_max(ob, o); ab = r_max(ab, al);
+            if (v != r) { oa = r_max(oa, o); aa = r_max(aa, al); }
+        }
+        if (has_add && k != r) {
+            const int dx = a.x - gk.x, dy = a.y - gk.y, d2 = dx * dx + dy * dy;
+            if (d2 <= m.ov_d2) oa = r_max(oa, pair_overlap(m, gk, ga, d2, sx, sy));
+            if (d2 <= m.al_d2) aa = r_max(aa, align_magnitude(gk, ga, m.rewarding));
+        }
+        // only objects that can be affected have meaningful unit terms; the others cancel exactly (same ov/al)
+        if (k == r) acc -= f_obj(m, w, k, ob, ab);
+        else if (oa != ob || aa != ab) acc += f_obj(m, w, k, oa, aa) - f_obj(m, w, k, ob, ab);
+    }
+    acc = warp_sum(acc);
+    if (has_add) {
+        R oa = 0, aa = 0;
+        for (int v = lane; v < n; v += 32) {
+            if (v == r || !(w.flags[v] & W2_ALIVE)) continue;
+            const int dx = w.x[v] - a.x, dy = w.y[v] - a.y, d2 = dx * dx + dy * dy;
+            if (d2 > m.max_d2) continue;
+            const Geo<R> gv = geo_w(w, v);
+            if (d2 <= m.ov_d2) oa = r_max(oa, pair_overlap(m, ga, gv, d2, sx, sy));
+            if (d2 <= m.al_d2) aa = r_max(aa, align_magnitude(ga, gv, m.rewarding));
+        }
+        oa = warp_max(oa); aa = warp_max(aa);
+        Terms<R> t;
+        t.pos = a.pos;
+        shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
+        t.ov = oa; t.al = (m.rewarding ? (R)-1 : (R)1) * aa;
+        t.area = area_prior<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.target_ratio - a.ratio);
+        acc += combine(m, t);
+    }
+    return acc;
+}
+
+// kernel-choice probabilities of a window holding n objects: the reference mixture (make_kernels.py:76-86) when
+// n >= 1; births only (renormalised) when the window is empty, where every other kernel is the empty perturbation.
+__device__ __forceinline__ float pk_of(const KernDev &k, int kernel, int n) {
+    if (n > 0) return (float)k.p[kernel];
+    if (kernel == 0 || kernel == 2) return (float)(k.p[kernel] / (k.p[0] + k.p[2]));
+    return 0.f;
+}
+
+// j-th (0-based) alive window object among the staged entries
+template <typename R>
+__device__ __forceinline__ int pick_window_object(const WinState<R> &w, int j, int lane) {
+    const int n = w.n;
+    for (int b = 0; b < n; b += 32) {
+        const int k = b + lane;
+        const bool in = k < n && (w.flags[k] & (W2_ALIVE | W2_WIN)) == (W2_ALIVE | W2_WIN);
+        const uint32_t bal = __ballot_sync(MPP_FULL, in);
+        const int cnt = __popc(bal);
+        if (j < cnt) return b + __fns(bal, 0, j + 1);
+        j -= cnt;
+    }
+    return -1;
+}
+
+template <typename R>
+struct Eval {  // outcome of evaluating one proposal (warp-uniform)
+    int kernel, r;
+    bool has_add, evaluated, accept;
+    Cand<R> a;
+};
+
+// Draws and evaluates proposal number `it` of this window's chain against the staged state (read-only).
+template <typename R>
+__device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
+                                  float temp, int lane, R *sx, R *sy, Eval<R> *e, float *dbg_maxdiff) {
+    Philox rng(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u);
+    const uint4 q0 = rng.next(), q1 = rng.next();
+    const ModelDev &m = c.m;
+    const int nc = w.n_win;
+    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false;
+    // kernel draw
+    int kernel;
+    {
+        const float uk = u01f(q0.x);
+        if (nc > 0) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += (float)c.k.p[k]; if (uk < acc) { kernel = k; break; } } }
+        else kernel = uk < (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])) ? 0 : 2;
+    }
+    e->kernel = kernel;
+    const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
+    const float q_unif = ((float)wx * (float)wy) / ((float)c.H * (float)c.W);
+    const float q_data = (float)(w.win_mass / c.cell_cdf[c.ncell - 1]);
+    int r = -1;
+    if (kernel != 0 && kernel != 2) {
+        r = pick_window_object(w, min(nc - 1, (int)(u01f(q0.y) * (float)nc)), lane);
+        if (r < 0) return;  // cannot happen (nc > 0)
+    }
+    e->r = r;
+    Cand<R> &a = e->a;
+    float log_ratio = 0.f;  // log(bwd) - log(fwd)
+    bool valid = true;
+    float pn[3], dm[3];
+    switch (kernel) {
+    case 0: {  // uniform birth in the window
+        a.x = w.x0 + min(wx - 1, (int)(u01f(q0.z) * (float)wx));
+        a.y = w.y0 + min(wy - 1, (int)(u01f(q0.w) * (float)wy));
+        a.size = (R)(u01f(q1.x) * 32.0f); a.ratio = (R)u01f(q1.y); a.angle = (R)(u01f(q1.z) * 3.14159265358979f);
+        a.cls = pack_cls(value_to_class<R>(0, a.size), value_to_class<R>(1, a.ratio), value_to_class<R>(2, a.angle));
+        pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
+        const float fwd = pk_of(c.k, 0, nc) / ((float)c.k.intensity * q_unif);
+        const float bwd = pk_of(c.k, 1, nc + 1) / (float)(nc + 1);
+        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        e->has_add = true;
+        break;
+    }
+    case 1: {  // uniform death
+        const float fwd = pk_of(c.k, 1, nc) / (float)nc;
+        const float bwd = pk_of(c.k, 0, nc - 1) / ((float)c.k.intensity * q_unif);
+        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        break;
+    }
+    case 2: {  // data-driven birth in the window
+        if (!(w.win_mass > 0.0)) { valid = false; break; }
+        const int row = warp_pick(lane < wx ? w.row_mass[lane] : 0.f, u01f(q0.z), lane, nullptr);
+        const float dv = lane < wy ? __ldg(c.det + (size_t)(w.x0 + row) * c.W + w.y0 + lane) : 0.f;
+        const int col = warp_pick(dv, u01f(q0.w), lane, nullptr);
+        a.x = w.x0 + row; a.y = w.y0 + col;
+        const float v0 = __ldg(mark_row(c, 0, a.x, a.y) + lane), v1 = __ldg(mark_row(c, 1, a.x, a.y) + lane), v2 = __ldg(mark_row(c, 2, a.x, a.y) + lane);
+        float s0, s1, s2;
+        const int c0 = warp_pick(v0, u01f(q1.x), lane, &s0), c1 = warp_pick(v1, u01f(q1.y), lane, &s1), c2 = warp_pick(v2, u01f(q1.z), lane, &s2);
+        const float p0 = __shfl_sync(MPP_FULL, v0, c0), p1 = __shfl_sync(MPP_FULL, v1, c1), p2 = __shfl_sync(MPP_FULL, v2, c2);
+        a.cls = pack_cls(c0, c1, c2);
+        a.size = mark_edge<R>(0, c0); a.ratio = mark_edge<R>(1, c1); a.angle = mark_edge<R>(2, c2);
+        a.detv = __shfl_sync(MPP_FULL, dv, col);
+        pn[0] = p0 / s0; pn[1] = p1 / s1; pn[2] = p2 / s2;
+        dm[0] = mark_energy_f32(m, 0, p0); dm[1] = mark_energy_f32(m, 1, p1); dm[2] = mark_energy_f32(m, 2, p2);
+        const float fwd = pk_of(c.k, 2, nc) * dens_of(c, a.detv, pn[0], pn[1], pn[2]) / ((float)c.k.intensity * q_data);
+        const float bwd = pk_of(c.k, 3, nc + 1) / (float)(nc + 1);
+        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        e->has_add = true;
+        break;
+    }
+    case 3: {  // data-driven death
+        if (!(w.win_mass > 0.0)) { valid = false; break; }
+        const float fwd = pk_of(c.k, 3, nc) / (float)nc;
+        const float bwd = pk_of(c.k, 2, nc - 1) * dens_of(c, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]) / ((float)c.k.intensity * q_data);
+        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        break;
+    }
+    case 4: {  // gaussian translation (symmetric: the proposal densities cancel)
+        double d0, d1;
+        box_muller(q0.z, q0.w, q1.x, q1.y, &d0, &d1);
+        const int nx_ = min(max((int)((double)w.x[r] + d0 * c.k.trl_sigma), 0), c.H - 1);
+        const int ny_ = min(max((int)((double)w.y[r] + d1 * c.k.trl_sigma), 0), c.W - 1);
+        if (nx_ < w.x0 || nx_ >= w.x1 || ny_ < w.y0 || ny_ >= w.y1) { valid = false; break; }
+        a.x = nx_; a.y = ny_; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
+        e->has_add = true;
+        break;
+    }
+    case 5: {  // data-driven translation in the 17x17 window around the object
+        const int md = c.k.trl_max_delta;
+        const int X0 = max(0, w.x[r] - md), X1 = min(w.x[r] + md + 1, c.H), Y0 = max(0, w.y[r] - md), Y1 = min(w.y[r] + md + 1, c.W);
+        const size_t pitch = (size_t)c.W + 1;
+        float rs = 0.f;
+        if (lane < X1 - X0) rs = (float)(c.rowcum[(size_t)(X0 + lane) * pitch + Y1] - c.rowcum[(size_t)(X0 + lane) * pitch + Y0]);
+        float tot_s;
+        const int row = warp_pick(rs, u01f(q0.z), lane, &tot_s);
+        if (!(tot_s > 0.f)) { valid = false; break; }
+        const float dv = lane < Y1 - Y0 ? __ldg(c.det + (size_t)(X0 + row) * c.W + Y0 + lane) : 0.f;
+        const int col = warp_pick(dv, u01f(q0.w), lane, nullptr);
+        const int ex = X0 + row, ey = Y0 + col;
+        if (ex < w.x0 || ex >= w.x1 || ey < w.y0 || ey >= w.y1) { valid = false; break; }
+        a.x = ex; a.y = ey; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        // backward window (around the end point) + the maps at the end point, one round trip
+        const int BX0 = max(0, ex - md), BX1 = min(ex + md + 1, c.H), BY0 = max(0, ey - md), BY1 = min(ey + md + 1, c.W);
+        float rb = 0.f;
+        if (lane < BX1 - BX0) rb = (float)(c.rowcum[(size_t)(BX0 + lane) * pitch + BY1] - c.rowcum[(size_t)(BX0 + lane) * pitch + BY0]);
+        pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
+        const float tot_e = warp_sum(rb);
+        const float fwd = a.detv / tot_s, bwd = w.detv[r] / tot_e;  // p_kernel / n cancel
+        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        e->has_add = true;
+        break;
+    }
+    default: {  // 6: gaussian mark transform (symmetric), 7: data-driven mark transform
+        const int pid = min(2, (int)(u01f(q0.z) * 3.0f));
+        const float v = __ldg(mark_row(c, pid, w.x[r], w.y[r]) + lane);
+        float s;
+        int ncls;
+        R nv;
+        const int ocls = cls_of(w.cls[r], pid);
+        if (kernel == 6) {
+            double d0, d1;
+            box_muller(q0.w, q1.x, q1.y, q1.z, &d0, &d1);
+            nv = (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r])) + (R)(d0 * c.k.trf_sigma[pid]);
+            const R vmax = (R)mark_vmax(pid);
+            if (pid == 2) { nv = nv - r_floor(nv / vmax) * vmax; if (!(nv < vmax) || nv < 0) nv = 0; }
+            else nv = r_min(r_max(nv, (R)0), vmax);
+            ncls = value_to_class<R>(pid, nv);
+            s = warp_sum(v);
+        } else {
+            ncls = warp_pick(v, u01f(q0.w), lane, &s);
+            nv = mark_edge<R>(pid, ncls);
+            const float pf = __shfl_sync(MPP_FULL, v, ncls) / s, pb = __shfl_sync(MPP_FULL, v, ocls) / s;
+            log_ratio = logf(pb + W2_EPS) - logf(pf + W2_EPS);  // p_kernel / n cancel
+        }
+        const float pnew = __shfl_sync(MPP_FULL, v, ncls);
+        a.x = w.x[r]; a.y = w.y[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        if (pid == 0) a.size = nv; else if (pid == 1) a.ratio = nv; else a.angle = nv;
+        a.cls = (w.cls[r] & ~(0xffu << (8 * pid))) | ((uint32_t)ncls << (8 * pid));
+        a.detv = w.detv[r];
+        pn[0] = w.pn0[r]; pn[1] = w.pn1[r]; pn[2] = w.pn2[r];
+        dm[0] = (float)w.dm0[r]; dm[1] = (float)w.dm1[r]; dm[2] = (float)w.dm2[r];
+        pn[pid] = pnew / s;
+        dm[pid] = mark_energy_f32(m, pid, pnew);
+        e->has_add = true;
+        break;
+    }
+    }
+    if (!valid) { e->has_add = false; return; }
+    if (e->has_add) {
+        a.pos = (R)position_energy_f32(a.detv, m.pos_thr);
+        a.dm0 = (R)dm[0]; a.dm1 = (R)dm[1]; a.dm2 = (R)dm[2];
+        a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
+        const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
+        a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+        if (r >= 0 && a.angle == w.angle[r]) {
+            a.ca = w.ca[r]; a.sa = w.sa[r];
+        } else {
+            r_sincos(a.angle, &a.sa, &a.ca);
+        }
+        // capacity of the destination storage cell (MPP_CELL_CAPACITY slots)
+        const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
+        uint32_t dmk = w.cmask[ci];
+        if (r >= 0 && w.handle[r] != MPP_NO_OBJECT && (int)(w.handle[r] >> 5) == w.ccell[ci]) dmk &= ~(1u << (w.handle[r] & 31));
+        if (dmk == 0xffffffffu) { e->has_add = false; return; }
+    }
+    const R de = delta_staged(m, w, r, e->has_add, a, lane, sx, sy);
+#ifndef MPP_TRACE
+    if (dbg_maxdiff) {
+        const R db = delta_brute(m, w, r, e->has_add, a, lane, sx, sy);
+        const float diff = fabsf((float)(de - db));
+        if (lane == 0) atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
+    }
+#endif
+    const float la = -(float)de / temp + log_ratio;
+    e->evaluated = true;
+    e->accept = logf(u01f(q1.w) + W2_EPS) < la;
+#ifdef MPP_TRACE
+    if (dbg_maxdiff && lane == 0) {
+        float *tr = dbg_maxdiff + 8;
+        const int slot = atomicAdd(reinterpret_cast<int *>(dbg_maxdiff + 1), 1);
+        if (slot < 4000) {
+            float *o = tr + slot * 10;
+            o[0] = (float)win_id; o[1] = (float)it; o[2] = (float)kernel; o[3] = (float)r; o[4] = (float)de; o[5] = la;
+            o[6] = logf(u01f(q1.w) + W2_EPS); o[7] = e->accept ? 1.f : 0.f; o[8] = (float)nc; o[9] = log_ratio;
+        }
+    }
+#endif
+}
+
+// Applies an accepted proposal to the staged state and to the storage cells (executed by one warp).
+template <typename R>
+__device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy) {
+    const ModelDev &m = c.m;
+    const int r = e.r;
+    int rx = 0, ry = 0;
+    if (r >= 0) {
+        rx = w.x[r]; ry = w.y[r];
+        if (lane == 0) {
+            w.flags[r] = 0;
+            const uint32_t h = w.handle[r];
+            for (int q = 0; q < 4; ++q)
+                if (w.ccell[q] == (int)(h >> 5)) { w.cmask[q] &= ~(1u << (h & 31)); __stcg(c.mask + w.ccell[q], w.cmask[q]); }
+            w.n_win -= 1; w.dn -= 1;
+        }
+    }
+    int s = -1;
+    if (e.has_add) {
+        // free staged slot: the removed entry if any, else the first dead entry, else append
+        s = r;
+        if (s < 0) {
+            const int n = w.n;
+            for (int b = 0; b < n && s < 0; b += 32) {
+                const uint32_t bal = __ballot_sync(MPP_FULL, b + lane < n && !(w.flags[b + lane] & W2_ALIVE));
+                if (bal) s = b + __ffs(bal) - 1;
+            }
+            if (s < 0) s = n;  // n < W2_K is guaranteed by the caller
+        }
+        if (lane == 0) {
+            const Cand<R> &a = e.a;
+            if (s == w.n) w.n = s + 1;
+            const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
+            const int slot = __ffs(~w.cmask[ci]) - 1;
+            const uint32_t h = (uint32_t)w.ccell[ci] * 32u + slot;
+            w.x[s] = a.x; w.y[s] = a.y; w.cls[s] = a.cls; w.handle[s] = h; w.uid[s] = w.uid_base + (uint32_t)it;
+            w.size[s] = a.size; w.ratio[s] = a.ratio; w.angle[s] = a.angle;
+            w.hl[s] = a.hl; w.hw[s] = a.hw; w.ca[s] = a.ca; w.sa[s] = a.sa;
+            w.pos[s] = a.pos; w.dm0[s] = a.dm0; w.dm1[s] = a.dm1; w.dm2[s] = a.dm2;
+            shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &w.tm0[s], &w.tm1[s], &w.tm2[s]);
+            w.detv[s] = a.detv; w.pn0[s] = a.pn0; w.pn1[s] = a.pn1; w.pn2[s] = a.pn2;
+            w.flags[s] = W2_ALIVE | W2_WIN | W2_INNER;
+            w.n_win += 1; w.dn += 1;
+            Rec<R> rec;
+            rec.x = a.x; rec.y = a.y; rec.cls = a.cls; rec.uid = w.uid[s];
+            rec.size = a.size; rec.ratio = a.ratio; rec.angle = a.angle;
+            rec.e_pos = a.pos; rec.e_m[0] = w.tm0[s]; rec.e_m[1] = w.tm1[s]; rec.e_m[2] = w.tm2[s];
+            rec.hl = a.hl; rec.hw = a.hw; rec.ca = a.ca; rec.sa = a.sa; rec.pad = 0;
+            store_rec(c.recs + h, rec);
+            __threadfence();  // a concurrent window staging this cell must never see the mask bit before the record
+            w.cmask[ci] |= 1u << slot;
+            __stcg(c.mask + w.ccell[ci], w.cmask[ci]);
+        }
+    }
+    __syncwarp();
+    // refresh the reductions of everything within reach of the change (and of the new object)
+    const int n = w.n;
+    for (int k = lane; k < n; k += 32) {
+        if (!(w.flags[k] & W2_ALIVE) || !(w.flags[k] & W2_INNER)) continue;
+        bool need = k == s;
+        if (r >= 0) { const int dx = w.x[k] - rx, dy = w.y[k] - ry; need |= dx * dx + dy * dy <= m.max_d2; }
+        if (s >= 0) { const int dx = w.x[k] - w.x[s], dy = w.y[k] - w.y[s]; need |= dx * dx + dy * dy <= m.max_d2; }
+        if (need) recompute_top2(m, w, k, sx, sy);
+    }
+    __syncwarp();
+}
+
+template <typename R, int NW>
+__global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp,
+                                                   uint64_t seed, uint64_t sweep_id, uint32_t uid_base, float *dbg_maxdiff) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
+    R *clip = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    R *sx = clip + (size_t)warp * (2 * 2 * 9 * 32) + lane, *sy = sx + 2 * 9 * 32;
+    const int a = blockIdx.x;
+    if (a >= n_wi * n_wj) return;
+    const int wi = ci + 3 * (a / n_wj), wj = cj + 3 * (a % n_wj);
+    const uint32_t win_id = (uint32_t)wi * 65536u + (uint32_t)wj;
+    const ModelDev &m = c.m;
+
+    // ------------------------------------------------------------------ staging (warp 0)
+    if (warp == 0) {
+        const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
+        const int x0 = max(px0, 0), x1 = min(px0 + 32, c.H), y0 = max(py0, 0), y1 = min(py0 + 32, c.W);
+        if (lane == 0) {
+            w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
+            w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
+            w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0;
+            w.uid_base = uid_base + (uint32_t)a * (uint32_t)per_visit;
+            for (int q = 0; q < 4; ++q) {
+                const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
+                const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);
+                w.ccell[q] = ok ? cy + cx * c.ny : -1;
+                w.cmask[q] = ok ? __ldcg(c.mask + cy + cx * c.ny) : 0xffffffffu;
+            }
+        }
+        // detection mass of the window rows
+        {
+            const size_t pitch = (size_t)c.W + 1;
+            double rm = 0.0;
+            if (lane < x1 - x0) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
+            w.row_mass[lane] = (float)rm;
+            const double tot = warp_sum(rm);
+            if (lane == 0) w.win_mass = tot;
+        }
+        // objects of the storage cells covering [x0-64, x1+64) x [y0-64, y1+64).
+        // Phase A: collect (handle, position key, uid) of the objects inside that box (16-byte record heads only).
+        const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
+        const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
+        int n = 0;
+        for (int b = 0; b < ncells; b += 32) {
+            const int k = b + lane;
+            int cell = 0;
+            uint32_t msk = 0;
+            if (k < ncells) { cell = (sy0 + k % ncw) + (sx0 + k / ncw) * c.ny; msk = __ldcg(c.mask + cell); }
+            uint32_t any = __ballot_sync(MPP_FULL, msk != 0);
+            while (any) {
+                uint32_t h = 0;
+                int4 head = make_int4(0, 0, 0, 0);
+                bool keep = false;
+                if (msk) {
+                    const int slot = __ffs(msk) - 1;
+                    msk &= msk - 1;
+                    h = (uint32_t)cell * 32u + slot;
+                    head = __ldcg(reinterpret_cast<const int4 *>(c.recs + h));
+                    keep = head.x >= x0 - 64 && head.x < x1 + 64 && head.y >= y0 - 64 && head.y < y1 + 64;
+                }
+                const uint32_t kb = __ballot_sync(MPP_FULL, keep);
+                if (keep) {
+                    const int p = n + __popc(kb & ((1u << lane) - 1));
+                    if (p < W2_K) { w.handle[p] = h; w.x[p] = head.x * 16384 + head.y; w.uid[p] = (uint32_t)head.w; }
+                }
+                n += __popc(kb);
+                any = __ballot_sync(MPP_FULL, msk != 0);
+            }
+        }
+        if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
+        __syncwarp();
+        // Phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
+        for (int k = lane; k < n; k += 32) {
+            const int key = w.x[k];
+            const uint32_t u = w.uid[k];
+            int rank = 0;
+            for (int v = 0; v < n; ++v) {
+                const int kv = w.x[v];
+                rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
+            }
+            w.order[rank] = w.handle[k];
+        }
+        __syncwarp();
+        // Phase C: one lane per object loads its full record
+        for (int p = lane; p < n; p += 32) {
+            const uint32_t h = w.order[p];
+            const Rec<R> rec = load_rec(c.recs + h);
+            const bool inw = rec.x >= x0 && rec.x < x1 && rec.y >= y0 && rec.y < y1;
+            const bool inner = rec.x >= x0 - 32 && rec.x < x1 + 32 && rec.y >= y0 - 32 && rec.y < y1 + 32;
+            w.x[p] = rec.x; w.y[p] = rec.y; w.cls[p] = rec.cls; w.handle[p] = h; w.uid[p] = rec.uid;
+            w.size[p] = rec.size; w.ratio[p] = rec.ratio; w.angle[p] = rec.angle;
+            w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa;
+            w.pos[p] = rec.e_pos; w.tm0[p] = rec.e_m[0]; w.tm1[p] = rec.e_m[1]; w.tm2[p] = rec.e_m[2];
+            w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
+        }
+        __syncwarp();
+        if (lane == 0) w.n = n;
+        // per-mark details of the window objects (needed by deaths, translations and mark transforms)
+        int nwin = 0;
+        for (int k = 0; k < n; ++k) {
+            if (!(w.flags[k] & W2_WIN)) continue;
+            ++nwin;
+            float detv, pn[3], dm[3];
+            pixel_info(c, w.x[k], w.y[k], w.cls[k], lane, &detv, pn, dm);
+            if (lane == 0) {
+                w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
+                w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
+            }
+        }
+        if (lane == 0) w.n_win = nwin;
+        __syncwarp();
+        // partner reductions of everything a move in the window can affect
+        for (int k = lane; k < n; k += 32)
+            if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, sx, sy);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ speculative proposal rounds
+    int it = 0;
+    while (it < per_visit) {
+        Eval<R> e;
+        const int mine = it + warp;
+        if (mine < per_visit) evaluate_proposal(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, &e, dbg_maxdiff);
+        else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; }
+        if (lane == 0) { w.res_accept[warp] = e.accept ? 1 : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
+        __syncthreads();
+        int first = NW;
+#pragma unroll
+        for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q]) first = q;
+        const int used = min(first + 1, min(NW, per_visit - it));  // proposals of the chain consumed by this round
+        if (warp == 0 && lane == 0) { int ev = 0; for (int q = 0; q < used; ++q) ev += w.res_eval[q]; w.n_eval += ev; w.n_done += used; }
+        if (first < NW && warp == first) {
+            if (lane == 0) {
+                w.n_acc += 1;
+                if (e.has_add && e.r < 0) w.n_birth += 1;
+                if (!e.has_add && e.r >= 0) w.n_death += 1;
+            }
+            if (w.n >= W2_K && e.has_add && e.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
+            else commit_proposal(c, w, e, mine, lane, sx, sy);
+        }
+        __syncthreads();
+        it += used;
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(c.counters + 0, (unsigned long long)w.n_done);
+        atomicAdd(c.counters + 1, (unsigned long long)w.n_acc);
+        atomicAdd(c.counters + 2, (unsigned long long)w.n_birth);
+        atomicAdd(c.counters + 3, (unsigned long long)w.n_death);
+        atomicAdd(c.counters + 4, (unsigned long long)w.n_eval);
+        if (w.dn) atomicAdd(c.n_objects, w.dn);
+    }
+}

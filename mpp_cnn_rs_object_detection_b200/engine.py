@@ -321,18 +321,34 @@ class Engine:
 
     def run_sweeps(self, n_sweeps: int, proposals_per_visit: int = 8, stride: int = 4, t0: float = 1.0, alpha_t: float = 1.0,
                    t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True):
-        cnt = (C.c_ulonglong * 4)()
+        cnt = (C.c_ulonglong * 8)()
         _lib.check(self.lib.mpp_run_sweeps(self.ctx, int(n_sweeps), int(proposals_per_visit), int(stride), float(t0),
                                            float(alpha_t), float(t_target), int(seed), int(sweep_offset),
                                            cnt if read_counters else None))
         self.launches += int(n_sweeps) * stride * stride
         return [int(v) for v in cnt] if read_counters else None
 
+    def run_windows(self, n_sweeps: int, proposals_per_visit: int = 16, n_warps: int = 4, t0: float = 1.0, alpha_t: float = 1.0,
+                    t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True, debug: bool = False):
+        """Production parallel sampler (mpp_run_windows): shifted 32-px windows, shared-memory resident visits, speculative
+        evaluation by `n_warps` warps.  Returns [proposals, accepted, births, deaths, evaluated, 0, 0, 0] (+ the largest
+        |fast - brute-force| Delta-energy difference when debug=True)."""
+        cnt = (C.c_ulonglong * 8)()
+        dbg = torch.zeros(1, dtype=torch.float32, device=self.device) if debug else None
+        _lib.check(self.lib.mpp_run_windows(self.ctx, int(n_sweeps), int(proposals_per_visit), int(n_warps), float(t0), float(alpha_t),
+                                            float(t_target), int(seed), int(sweep_offset), cnt if read_counters else None,
+                                            None if dbg is None else dbg.data_ptr()))
+        self.launches += int(n_sweeps) * 9
+        out = [int(v) for v in cnt] if read_counters else None
+        if debug:
+            return out, float(dbg.cpu().item())
+        return out
+
     def run_chain(self, n_steps: int, t0: float = 1.0, alpha_t: float = 1.0, t_target: float = 0.0, seed: int = 0,
                   step_offset: int = 0, trace: bool = False, read_counters: bool = True):
         """Sequential device chain with the reference's global kernels (RJMCMC.run, rjmcmc.py:83-181)."""
         tr = torch.zeros((max(n_steps, 1), _lib.STEP_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=self.device) if trace else None
-        cnt = (C.c_ulonglong * 4)()
+        cnt = (C.c_ulonglong * 8)()
         _lib.check(self.lib.mpp_run_chain(self.ctx, int(n_steps), float(t0), float(alpha_t), float(t_target), int(seed),
                                           int(step_offset), None if tr is None else tr.data_ptr(), cnt if read_counters else None))
         self.launches += 2 if n_steps > 0 else 0

@@ -1,0 +1,87 @@
+"""-m gpu: the production parallel sampler (mpp_run_windows).  Checks: the fast Delta-energy (top-2 reductions in shared
+memory) against its brute-force recomputation inside the kernel; independence of the chain from the speculation depth;
+integrity of the records it writes; and agreement of its stationary distribution with the sequential device chain."""
+import numpy as np
+import pytest
+
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(cfg, seed=5, shape=(192, 224), n_rect=60):
+    from mpp_cnn_rs_object_detection_b200 import synth
+    from tests.gpu_util import make_engine
+    objs, det, marks = synth.make_scene(seed, shape, n_rect)
+    eng = make_engine(cfg, det, marks, "fp32", intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    return objs, det, marks, eng
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_fast_delta_equals_brute_force(cfg):
+    objs, det, marks, eng = _scene(cfg)
+    cnt, maxdiff = eng.run_windows(40, proposals_per_visit=12, n_warps=4, t0=0.03, seed=3, debug=True)
+    assert cnt[0] > 0 and cnt[4] > 0 and cnt[1] > 0
+    assert maxdiff < 2e-5, maxdiff
+    assert len(eng) == len(objs) + cnt[2] - cnt[3]
+
+
+def test_chain_is_independent_of_speculation_depth():
+    finals = []
+    for nw in (1, 2, 4, 8):
+        objs, det, marks, eng = _scene("legacy")
+        cnt = eng.run_windows(25, proposals_per_visit=10, n_warps=nw, t0=0.03, seed=9)
+        h, xy, mk, uid = eng.read_objects()
+        order = np.lexsort((xy[:, 1], xy[:, 0]))
+        finals.append((cnt[:5], xy[order], mk[order]))
+    for f in finals[1:]:
+        assert f[0] == finals[0][0]
+        np.testing.assert_array_equal(f[1], finals[0][1])
+        np.testing.assert_array_equal(f[2], finals[0][2])
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_written_records_are_consistent(cfg):
+    """After many accepted moves the cached unit energies / geometry of every stored record equal a fresh insertion."""
+    from tests.gpu_util import make_engine
+    objs, det, marks, eng = _scene(cfg)
+    eng.run_windows(60, proposals_per_visit=16, n_warps=4, t0=0.05, seed=4)
+    h, xy, mk, uid = eng.read_objects()
+    assert len(set(uid.tolist())) == len(uid)
+    vec, comb, raw, tot = eng.energy_vectors(h)
+    fresh = make_engine(cfg, det, marks, "fp32")
+    h2 = fresh.add_objects(xy, mk)
+    vec2, comb2, raw2, tot2 = fresh.energy_vectors(h2)
+    np.testing.assert_allclose(vec, vec2, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(comb, comb2, rtol=1e-6, atol=1e-6)
+    assert np.all((xy[:, 0] >= 0) & (xy[:, 0] < det.shape[0]) & (xy[:, 1] >= 0) & (xy[:, 1] < det.shape[1]))
+
+
+def _batch_se(x, nb=20):
+    x = np.asarray(x, dtype=np.float64)
+    m = len(x) // nb
+    b = x[:m * nb].reshape(nb, m).mean(1)
+    return x.mean(), b.std(ddof=1) / np.sqrt(nb)
+
+
+def test_stationary_distribution_matches_sequential_chain():
+    from mpp_cnn_rs_object_detection_b200 import synth
+    from tests.gpu_util import make_engine
+    temp = 0.3
+    objs, det, marks = synth.make_scene(11, (64, 96), 8)
+    eng = make_engine("legacy", det, marks, "fp32", intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    eng.run_chain(20000, t0=temp, seed=1)
+    _, trace = eng.run_chain(600000, t0=temp, seed=1, step_offset=20000, trace=True)
+    mb, sb = _batch_se(trace["n_after"][::10])
+    e2 = make_engine("legacy", det, marks, "fp32", intensity=max(1, len(objs)))
+    e2.add_objects(objs[:, :2], objs[:, 2:5])
+    e2.run_windows(300, proposals_per_visit=4, n_warps=2, t0=temp, seed=2)
+    nc = []
+    for s in range(6000):
+        e2.run_windows(1, proposals_per_visit=4, n_warps=2, t0=temp, seed=2, sweep_offset=300 + s, read_counters=False)
+        nc.append(len(e2))
+    mc, sc = _batch_se(nc)
+    print(f"\nobject count at T={temp}: device chain {mb:.3f}+-{sb:.3f} | windows {mc:.3f}+-{sc:.3f}")
+    assert abs(mb - mc) < 5 * np.hypot(sb, sc) + 0.04, (mb, mc)

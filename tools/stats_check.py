@@ -36,6 +36,16 @@ def main():
                 nc.append(len(e2))
             mc, sc = batch_se(nc)
             res.append(f"sweeps(stride {stride}, pv {pv}) {mc:.4f}+-{sc:.4f}")
+        for nw, pv in ((4, 8), (1, 2)):
+            e2 = make_engine(cfg, det, marks, "fp32", intensity=max(1, n0))
+            e2.add_objects(objs[:, :2], objs[:, 2:5])
+            e2.run_windows(1000, proposals_per_visit=pv, n_warps=nw, t0=temp, seed=2)
+            nc = []
+            for s in range(20000):
+                e2.run_windows(1, proposals_per_visit=pv, n_warps=nw, t0=temp, seed=2, sweep_offset=1000 + s, read_counters=False)
+                nc.append(len(e2))
+            mc, sc = batch_se(nc)
+            res.append(f"windows(nw {nw}, pv {pv}) {mc:.4f}+-{sc:.4f}")
         print(f"T={temp} shape={shape} n0={n0}: " + " | ".join(res), flush=True)
 
 

@@ -1,0 +1,43 @@
+"""Times mpp_run_windows on the bench scene for several (n_warps, proposals_per_visit) settings (development tool)."""
+import sys, os, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from mpp_cnn_rs_object_detection_b200 import synth
+from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+temp = 0.02
+dev = torch.device("cuda", 0)
+n_rect = int(round(2600 * size * size / 2048.0 ** 2))
+objs, det, marks = synth.make_scene_torch(0, (size, size), n_rect, dev)
+C, H = bench.CALIB_HRCM, bench.HRC
+spec = ModelSpec(setup="legacy", pos_threshold=C["detection_threshold"], remap_coefs=C["coefs"], remap_intercepts=C["intercepts"],
+                 min_area=C["min_area"], max_area=C["max_area"], combinator="hierarchical",
+                 comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
+for nw, pv in ((1, 8), (1, 16), (2, 16), (4, 8), (4, 16), (4, 32), (8, 16), (8, 32), (8, 64)):
+    eng = Engine((size, size), device=dev)
+    eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    eng.run_windows(5, pv, nw, t0=temp, seed=1)
+    sweeps = 20
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run_windows(sweeps, pv, nw, t0=temp, seed=1, sweep_offset=5, read_counters=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    c = eng.run_windows(0, pv, nw, t0=temp)
+    print(f"nw={nw} pv={pv}: {ms / sweeps / 9 * 1e3:.1f} us/launch, attempted {c[0] / ms / 1e3:.1f} M/s, evaluated {c[4] / ms / 1e3:.1f} M/s, "
+          f"acc {c[1] / max(1, c[4]):.3f}, n={len(eng)}", flush=True)
+    eng.close()
+# v1 for comparison
+eng = Engine((size, size), device=dev)
+eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
+eng.add_objects(objs[:, :2], objs[:, 2:5])
+eng.run_sweeps(5, 8, 3, t0=temp, seed=1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); eng.run_sweeps(20, 8, 3, t0=temp, seed=1, sweep_offset=5, read_counters=False); e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1); c = eng.run_sweeps(0, 8, 3, t0=temp)
+print(f"v1 cells pv=8: {ms / 20 / 9 * 1e3:.1f} us/launch, attempted {c[0] / ms / 1e3:.1f} M/s, evaluated {c[4] / ms / 1e3:.1f} M/s, n={len(eng)}")
