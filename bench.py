@@ -55,8 +55,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--n-rect", type=int, default=0, help="candidate rectangles (0: 2600 per 2048^2, scaled by area)")
-    ap.add_argument("--sweeps", type=int, default=75)
-    ap.add_argument("--per-visit", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=36)
+    ap.add_argument("--per-visit", type=int, default=16)
+    ap.add_argument("--warps", type=int, default=4, help="warps per window (speculation depth) of the window sampler")
+    ap.add_argument("--sampler", default="windows", choices=["windows", "cells"],
+                    help="windows: mpp_run_windows (production); cells: mpp_run_sweeps (first-generation aligned cells)")
     ap.add_argument("--stride", type=int, default=3)
     ap.add_argument("--temperature", type=float, default=0.02)
     ap.add_argument("--seed", type=int, default=0)
@@ -253,13 +256,19 @@ def run_b200(args):
     eng.add_objects(objs[:, :2], objs[:, 2:5])
     n0 = len(eng)
 
+    def run(n_sweeps, seed_off, read_counters=False):
+        if args.sampler == "windows":
+            return eng.run_windows(n_sweeps, args.per_visit, args.warps, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
+                                   sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
+        return eng.run_sweeps(n_sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
+                              sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
+
     def step(seed_off):
-        eng.run_sweeps(args.sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
-                       sweep_offset=seed_off * args.sweeps, read_counters=False)
+        run(args.sweeps, seed_off)
 
     for s in range(args.warmup):
         step(s)
-    eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)  # reads + resets the counters
+    run(0, 0, read_counters=True)  # reads + resets the counters
     launches0 = eng.launches
     clocks = ClockSampler(local)
     barrier()
@@ -274,9 +283,12 @@ def run_b200(args):
     barrier()
     clk = clocks.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
-    cnt = eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
+    cnt = run(0, 0, read_counters=True)
     gpu_launches = eng.launches - launches0
-    proposals = sum_over_ranks(float(cnt[0]))
+    # a proposal = one RJMCMC step whose Delta-energy was evaluated (counter 4); attempts that end before the energy
+    # evaluation (empty perturbations, moves leaving their window) are NOT counted
+    proposals = sum_over_ranks(float(cnt[4]))
+    attempted = sum_over_ranks(float(cnt[0]))
     accepted = sum_over_ranks(float(cnt[1]))
     n1 = len(eng)
     value = proposals / (ms * 1e-3)
@@ -298,14 +310,13 @@ def run_b200(args):
             eng.clear()
             eng.set_maps(det_d, marks_d)
             eng.add_objects(xy_h, mk_h)
-            eng.run_sweeps(args.sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
-                           sweep_offset=seed_off * args.sweeps, read_counters=False)
+            run(args.sweeps, seed_off)
             hd, xy, mk, uid = eng.read_objects()
             d2h = hd.nbytes + xy.nbytes + mk.nbytes + uid.nbytes
 
         e2e_steps = max(1, min(args.steps, 3))
         e2e_step(1000)
-        eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
+        run(0, 0, read_counters=True)
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -314,8 +325,8 @@ def run_b200(args):
         torch.cuda.synchronize()
         t_e2e = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        cnt2 = eng.run_sweeps(0, args.per_visit, args.stride, t0=args.temperature)
-        p2 = sum_over_ranks(float(cnt2[0]))
+        cnt2 = run(0, 0, read_counters=True)
+        p2 = sum_over_ranks(float(cnt2[4]))
         e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4 + xy_h.nbytes + mk_h.nbytes + 4 * len(xy_h)),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
                "timer": "host wall clock around H2D + sampler + D2H, max over ranks"}
@@ -327,9 +338,9 @@ def run_b200(args):
     acc = accepted / max(1.0, proposals)
     bpp = bytes_per_proposal(k2, acc, h, w, kernel_probabilities())
     peak, peak_src = measured_peak()
-    sweep_launches = args.steps * args.sweeps * args.stride * args.stride
+    sweep_launches = args.steps * args.sweeps * (9 if args.sampler == "windows" else args.stride * args.stride)
     achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_sweep2<float,%d>" % args.warps if args.sampler == "windows" else "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
                 "proposals_per_launch": proposals / world / sweep_launches, "us_per_launch": 1e3 * ms / sweep_launches,
                 "note": "latency/parallelism-bound Markov chain: see DESIGN.md"}
@@ -337,8 +348,10 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sweeps_per_step": args.sweeps, "proposals_per_visit": args.per_visit,
-                       "colour_stride": args.stride, "objects_start": n0, "objects_end": n1, "acceptance": acc,
+            "config": {"workload": workload_name(args), "sampler": args.sampler, "sweeps_per_step": args.sweeps,
+                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "colour_stride": 3 if args.sampler == "windows" else args.stride,
+                       "attempted_per_step": attempted / args.steps,
+                       "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated (empty perturbations and moves leaving their window are not counted)", "objects_start": n0, "objects_end": n1, "acceptance": acc,
                        "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU",
                        "l2": "inputs larger than L2 (mark maps 3 x %.0f MB)" % (h * w * 32 * 4 / 1e6)},
             "ms_per_image": ms / args.steps, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline}

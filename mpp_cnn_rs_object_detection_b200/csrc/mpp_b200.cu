@@ -939,6 +939,37 @@ static int model_from_params(const mpp_model_params *p, ModelDev &m) {
     m.min_area = p->min_area; m.max_area = p->max_area; m.target_ratio = p->target_ratio;
     for (int i = 0; i < MPP_MAX_TERMS; ++i) m.w[i] = p->comb_w[i];
     m.bias = p->comb_bias; m.thr = p->comb_threshold;
+    {   // fold the combinator into the gated linear form used by the sweep kernels (see ModelDev)
+        const int n = m.n_terms;
+        double a0 = 0, b[MPP_MAX_TERMS] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0;
+        m.gate = 0; m.logistic = 0; m.gate_thr = (float)p->comb_threshold;
+        switch (p->combinator) {
+        case MPP_COMB_HIERARCHICAL:
+            a0 = m.w[5] * m.w[0]; b[1] = m.w[5] * m.w[1]; b[2] = m.w[6] * m.w[2]; b[3] = m.w[6] * m.w[3]; b[4] = m.w[6] * m.w[4];
+            c0 = m.bias; m.gate = 1;
+            break;
+        case MPP_COMB_MANUAL_HIERARCHICAL:
+            a0 = m.w[0]; for (int k = 1; k < n; ++k) b[k] = m.w[k];
+            m.gate = 1;
+            break;
+        case MPP_COMB_LOGISTIC:
+            a0 = m.w[0]; for (int k = 1; k < n; ++k) b[k] = m.w[k];
+            c0 = (double)n * m.bias; m.logistic = 1;
+            break;
+        default:
+            a0 = 1.0; for (int k = 1; k < n; ++k) b[k] = 1.0;
+            break;
+        }
+        m.c_pos = (float)a0; m.c_0 = (float)c0;
+        m.c_m0 = m.c_m1 = m.c_m2 = m.c_ov = m.c_al = m.c_area = m.c_ratio = 0.f;
+        if (p->setup == MPP_SETUP_LEGACY) { m.c_m0 = (float)b[1]; m.c_ov = (float)b[2]; m.c_al = (float)b[3]; m.c_area = (float)b[4]; }
+        else if (p->setup == MPP_SETUP_TOY) { m.c_ov = (float)b[1]; }
+        else {
+            m.c_m0 = (float)b[1]; m.c_m1 = (float)b[2]; m.c_m2 = (float)b[3]; m.c_ov = (float)b[4]; m.c_al = (float)b[5];
+            m.c_area = (float)b[6]; m.c_ratio = p->ratio_prior ? (float)b[7] : 0.f;
+        }
+        m.f_min_area = (float)p->min_area; m.f_max_area = (float)p->max_area; m.f_target_ratio = (float)p->target_ratio;
+    }
     return MPP_OK;
 }
 
@@ -1228,20 +1259,21 @@ static uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-template <typename R, int NW>
+template <typename R, int NW, bool DBG>
 static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp, uint64_t seed,
                                  uint64_t sweep_id, float *dbg) {
     const uint32_t uid_base = h->window_uid_next;
     h->window_uid_next += (uint32_t)(n_wi * n_wj * per_visit);
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;  // wrapped: stay in the upper half
-    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32) * sizeof(R);
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_sweep2<R, NW><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id, uid_base, dbg);
+    k_sweep2<R, NW, DBG><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id,
+                                                                  uid_base, dbg);
     return cudaGetLastError();
 }
 
@@ -1251,6 +1283,7 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
     if (n_sweeps < 0 || per_visit < 1 || per_visit > 64 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 64)");
     if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 1, 2, 4 or 8");
     if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
+    if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_windows: the window sampler is float32 only (use mpp_run_chain / mpp_replay for float64)");
     CUDA_TRY(cudaSetDevice(h->device));
     double temp = t0;
     for (int s = 0; s < n_sweeps; ++s) {
@@ -1263,9 +1296,9 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
                 const int n_wi = ci < nwx ? (nwx - ci + 2) / 3 : 0, n_wj = cj < nwy ? (nwy - cj + 2) / 3 : 0;
                 if (n_wi * n_wj == 0) continue;
                 cudaError_t e;
-#define MPP_LAUNCH_W(NWV) (h->precision == MPP_PRECISION_FP64 \
-        ? launch_sweep2<double, NWV>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff) \
-        : launch_sweep2<float, NWV>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff))
+#define MPP_LAUNCH_W(NWV) (debug_maxdiff \
+        ? launch_sweep2<float, NWV, true>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff) \
+        : launch_sweep2<float, NWV, false>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff))
                 switch (n_warps) {
                 case 1: e = MPP_LAUNCH_W(1); break;
                 case 2: e = MPP_LAUNCH_W(2); break;

@@ -32,15 +32,21 @@ struct WinState {
     int dn, n_acc, n_birth, n_death, n_eval, n_done;
     float row_mass[32];   // detection mass of each window row;  win_mass = their sum
     double win_mass;
+    // per-visit constants
+    float pkf[8];         // kernel-choice probabilities (make_kernels.py:76-86)
+    float pk_e0, pk_e2;   // ... of the two birth kernels when the window is empty (births only)
+    float lam_unif, lam_data;  // birth intensity of the window: Lambda * (share of the uniform / data-driven proposal mass)
+    float dens_scale;     // H * W * 32^3 / sum(det): RectangleSampler.get_point_density (shape_samplers.py:88,103-108)
+    int masks_dirty;
     int x[W2_K], y[W2_K];
     uint32_t cls[W2_K], handle[W2_K], uid[W2_K];
     R size[W2_K], ratio[W2_K], angle[W2_K];
-    R hl[W2_K], hw[W2_K], ca[W2_K], sa[W2_K];
+    R hl[W2_K], hw[W2_K], ca[W2_K], sa[W2_K], rad[W2_K];
     R pos[W2_K], tm0[W2_K], tm1[W2_K], tm2[W2_K];      // unit data terms as the combinator sees them
     R dm0[W2_K], dm1[W2_K], dm2[W2_K];                  // per-mark energies (window objects; legacy: before the mean)
     float detv[W2_K], pn0[W2_K], pn1[W2_K], pn2[W2_K];  // det value and normalised mark probabilities (window objects)
     R ov1[W2_K], ov2[W2_K], al1[W2_K], al2[W2_K];
-    short aov[W2_K], aal[W2_K];
+    short aov[W2_K], aal[W2_K], aov2[W2_K], aal2[W2_K];  // staged indices of the best / second-best partners
     unsigned char flags[W2_K];
     uint32_t order[W2_K];  // staging scratch: handles in canonical order
     // speculation results, one slot per warp
@@ -85,40 +91,51 @@ __device__ __forceinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32
     dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
 }
 
-// RectangleSampler.get_point_density (shape_samplers.py:103-108) from staged factors
-template <typename R>
-__device__ __forceinline__ float dens_of(const Ctx<R> &c, float detv, float pn0, float pn1, float pn2) {
-    return (detv / c.det_sum) * (pn0 * pn1 * pn2) * ((float)c.H * (float)c.W * 32768.0f);
-}
-
 template <typename R>
 __device__ __forceinline__ Geo<R> geo_w(const WinState<R> &w, int k) {
     Geo<R> g; g.x = w.x[k]; g.y = w.y[k]; g.hl = w.hl[k]; g.hw = w.hw[k]; g.ca = w.ca[k]; g.sa = w.sa[k];
     return g;
 }
 
+// RectangleSampler.get_point_density (shape_samplers.py:103-108) from staged factors
+template <typename R>
+__device__ __forceinline__ float dens_of(const WinState<R> &w, float detv, float pn0, float pn1, float pn2) {
+    return detv * (pn0 * pn1 * pn2) * w.dens_scale;
+}
+
+// overlap-kind pair value between staged entry k and an object with geometry gb / bounding radius rad_b; the
+// bounding-circle test is done inline so that the (out-of-line) polygon clip only runs for pairs that can intersect
+template <typename R>
+__device__ __forceinline__ R pair_ov_w(const ModelDev &m, const WinState<R> &w, int k, const Geo<R> &gb, R rad_b, int d2, R *sx, R *sy) {
+    if (m.setup == MPP_SETUP_TOY) return d2 <= m.toy_d2 ? (R)m.toy_pair : (R)0;
+    const R rr = w.rad[k] + rad_b;
+    if ((R)d2 > rr * rr * (R)1.0001) return (R)0;
+    return overlap_energy(geo_w(w, k), gb, sx, sy);
+}
+
 // top-2 partner reductions of staged entry k over every other alive staged entry (one lane, serial loop)
 template <typename R>
-__device__ void recompute_top2(const ModelDev &m, WinState<R> &w, int k, R *sx, R *sy) {
+__device__ __noinline__ void recompute_top2(const ModelDev &m, WinState<R> &w, int k, bool do_ov, bool do_al, R *sx, R *sy) {
     R o1 = 0, o2 = 0, a1 = 0, a2 = 0;
-    int ao = -1, aa = -1;
+    int ao = -1, aa = -1, ao2 = -1, aa2 = -1;
     const Geo<R> gk = geo_w(w, k);
+    const R rk = w.rad[k];
     const int n = w.n;
     for (int v = 0; v < n; ++v) {
         if (v == k || !(w.flags[v] & W2_ALIVE)) continue;
         const int dx = w.x[v] - gk.x, dy = w.y[v] - gk.y, d2 = dx * dx + dy * dy;
         if (d2 > m.max_d2) continue;
-        const Geo<R> gv = geo_w(w, v);
-        if (d2 <= m.ov_d2) {
-            const R o = pair_overlap(m, gk, gv, d2, sx, sy);
-            if (o > o1) { o2 = o1; o1 = o; ao = v; } else if (o > o2) o2 = o;
+        if (do_ov && d2 <= m.ov_d2) {
+            const R o = pair_ov_w(m, w, v, gk, rk, d2, sx, sy);
+            if (o > o1) { o2 = o1; ao2 = ao; o1 = o; ao = v; } else if (o > o2) { o2 = o; ao2 = v; }
         }
-        if (d2 <= m.al_d2) {
-            const R a = align_magnitude(gk, gv, m.rewarding);
-            if (a > a1) { a2 = a1; a1 = a; aa = v; } else if (a > a2) a2 = a;
+        if (do_al && d2 <= m.al_d2) {
+            const R a = align_magnitude(gk, geo_w(w, v), m.rewarding);
+            if (a > a1) { a2 = a1; aa2 = aa; a1 = a; aa = v; } else if (a > a2) { a2 = a; aa2 = v; }
         }
     }
-    w.ov1[k] = o1; w.ov2[k] = o2; w.al1[k] = a1; w.al2[k] = a2; w.aov[k] = (short)ao; w.aal[k] = (short)aa;
+    if (do_ov) { w.ov1[k] = o1; w.ov2[k] = o2; w.aov[k] = (short)ao; w.aov2[k] = (short)ao2; }
+    if (do_al) { w.al1[k] = a1; w.al2[k] = a2; w.aal[k] = (short)aa; w.aal2[k] = (short)aa2; }
 }
 
 template <typename R>
@@ -126,40 +143,45 @@ __device__ __forceinline__ R f_obj(const ModelDev &m, const WinState<R> &w, int 
     Terms<R> t;
     t.pos = w.pos[k]; t.m0 = w.tm0[k]; t.m1 = w.tm1[k]; t.m2 = w.tm2[k];
     t.ov = ov; t.al = (m.rewarding ? (R)-1 : (R)1) * al;
-    t.area = area_prior<R>(m, w.hl[k], w.hw[k]);
-    t.ratio = r_abs((R)m.target_ratio - w.ratio[k]);
-    return combine(m, t);
+    t.area = area_prior_fast<R>(m, w.hl[k], w.hw[k]);
+    t.ratio = r_abs((R)m.f_target_ratio - w.ratio[k]);
+    return combine_fast(m, t);
 }
 
 // Delta-energy of removing staged entry r (r < 0: none) and/or adding `a` (has_add), from the staged state only.
+// po / pa (per-warp scratch, W2_K entries each) receive the overlap / alignment pair values between every staged
+// entry and `a` (0 where out of reach) so that an accepted proposal can update the top-2 reductions incrementally.
 template <typename R>
-__device__ R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy) {
+__device__ R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy, R *po, R *pa) {
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    const R rad_a = has_add ? r_sqrt(a.hl * a.hl + a.hw * a.hw) : (R)0;
     const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
     R acc = 0, ov_add = 0, al_add = 0;
     const int n = w.n;
     for (int k = lane; k < n; k += 32) {
-        if (k == r || !(w.flags[k] & W2_ALIVE)) continue;
-        bool touched = false;
-        R ov_b = w.ov1[k], al_b = w.al1[k], ov_a = ov_b, al_a = al_b;
-        if (r >= 0) {
-            const int dx = w.x[k] - rx, dy = w.y[k] - ry;
-            if (dx * dx + dy * dy <= m.max_d2) {
-                touched = true;
-                if (w.aov[k] == r) ov_a = w.ov2[k];
-                if (w.aal[k] == r) al_a = w.al2[k];
+        R o = 0, al = 0;
+        if (k != r && (w.flags[k] & W2_ALIVE)) {
+            bool touched = false;
+            R ov_b = w.ov1[k], al_b = w.al1[k], ov_a = ov_b, al_a = al_b;
+            if (r >= 0) {
+                const int dx = w.x[k] - rx, dy = w.y[k] - ry;
+                if (dx * dx + dy * dy <= m.max_d2) {
+                    touched = true;
+                    if (w.aov[k] == r) ov_a = w.ov2[k];
+                    if (w.aal[k] == r) al_a = w.al2[k];
+                }
             }
-        }
-        if (has_add) {
-            const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
-            if (d2 <= m.max_d2) {
-                touched = true;
-                const Geo<R> gk = geo_w(w, k);
-                if (d2 <= m.ov_d2) { const R o = pair_overlap(m, gk, ga, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
-                if (d2 <= m.al_d2) { const R al = align_magnitude(gk, ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
+            if (has_add) {
+                const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
+                if (d2 <= m.max_d2) {
+                    touched = true;
+                    if (d2 <= m.ov_d2) { o = pair_ov_w(m, w, k, ga, rad_a, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
+                    if (d2 <= m.al_d2) { al = align_magnitude(geo_w(w, k), ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
+                }
             }
+            if (touched) acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, ov_b, al_b);
         }
-        if (touched) acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, ov_b, al_b);
+        if (has_add) { po[k] = o; pa[k] = al; }
     }
     acc = warp_sum(acc);
     if (has_add) {
@@ -168,9 +190,9 @@ __device__ R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool h
         t.pos = a.pos;
         shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
         t.ov = ov_add; t.al = (m.rewarding ? (R)-1 : (R)1) * al_add;
-        t.area = area_prior<R>(m, a.hl, a.hw);
-        t.ratio = r_abs((R)m.target_ratio - a.ratio);
-        acc += combine(m, t);
+        t.area = area_prior_fast<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
+        acc += combine_fast(m, t);
     }
     if (r >= 0) acc -= f_obj(m, w, r, w.ov1[r], w.al1[r]);
     return acc;
@@ -222,19 +244,27 @@ __device__ R delta_brute(const ModelDev &m, const WinState<R> &w, int r, bool ha
         t.pos = a.pos;
         shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
         t.ov = oa; t.al = (m.rewarding ? (R)-1 : (R)1) * aa;
-        t.area = area_prior<R>(m, a.hl, a.hw);
-        t.ratio = r_abs((R)m.target_ratio - a.ratio);
-        acc += combine(m, t);
+        t.area = area_prior_fast<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
+        acc += combine_fast(m, t);
     }
     return acc;
 }
 
+__device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float *n0, float *n1) {
+    const float u1 = u01f(a), u2 = u01f(b);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    *n0 = r * cs; *n1 = r * sn;
+}
+
 // kernel-choice probabilities of a window holding n objects: the reference mixture (make_kernels.py:76-86) when
 // n >= 1; births only (renormalised) when the window is empty, where every other kernel is the empty perturbation.
-__device__ __forceinline__ float pk_of(const KernDev &k, int kernel, int n) {
-    if (n > 0) return (float)k.p[kernel];
-    if (kernel == 0 || kernel == 2) return (float)(k.p[kernel] / (k.p[0] + k.p[2]));
-    return 0.f;
+template <typename R>
+__device__ __forceinline__ float pk_of(const WinState<R> &w, int kernel, int n) {
+    if (n > 0) return w.pkf[kernel];
+    return kernel == 0 ? w.pk_e0 : (kernel == 2 ? w.pk_e2 : 0.f);
 }
 
 // j-th (0-based) alive window object among the staged entries
@@ -260,9 +290,9 @@ struct Eval {  // outcome of evaluating one proposal (warp-uniform)
 };
 
 // Draws and evaluates proposal number `it` of this window's chain against the staged state (read-only).
-template <typename R>
+template <typename R, bool DBG>
 __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
-                                  float temp, int lane, R *sx, R *sy, Eval<R> *e, float *dbg_maxdiff) {
+                                  float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff) {
     Philox rng(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u);
     const uint4 q0 = rng.next(), q1 = rng.next();
     const ModelDev &m = c.m;
@@ -272,13 +302,11 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     int kernel;
     {
         const float uk = u01f(q0.x);
-        if (nc > 0) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += (float)c.k.p[k]; if (uk < acc) { kernel = k; break; } } }
-        else kernel = uk < (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])) ? 0 : 2;
+        if (nc > 0) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += w.pkf[k]; if (uk < acc) { kernel = k; break; } } }
+        else kernel = uk < w.pk_e0 ? 0 : 2;
     }
     e->kernel = kernel;
     const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
-    const float q_unif = ((float)wx * (float)wy) / ((float)c.H * (float)c.W);
-    const float q_data = (float)(w.win_mass / c.cell_cdf[c.ncell - 1]);
     int r = -1;
     if (kernel != 0 && kernel != 2) {
         r = pick_window_object(w, min(nc - 1, (int)(u01f(q0.y) * (float)nc)), lane);
@@ -296,16 +324,16 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         a.size = (R)(u01f(q1.x) * 32.0f); a.ratio = (R)u01f(q1.y); a.angle = (R)(u01f(q1.z) * 3.14159265358979f);
         a.cls = pack_cls(value_to_class<R>(0, a.size), value_to_class<R>(1, a.ratio), value_to_class<R>(2, a.angle));
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
-        const float fwd = pk_of(c.k, 0, nc) / ((float)c.k.intensity * q_unif);
-        const float bwd = pk_of(c.k, 1, nc + 1) / (float)(nc + 1);
-        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        const float fwd = pk_of(w, 0, nc) / w.lam_unif;
+        const float bwd = pk_of(w, 1, nc + 1) / (float)(nc + 1);
+        log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
     }
     case 1: {  // uniform death
-        const float fwd = pk_of(c.k, 1, nc) / (float)nc;
-        const float bwd = pk_of(c.k, 0, nc - 1) / ((float)c.k.intensity * q_unif);
-        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        const float fwd = pk_of(w, 1, nc) / (float)nc;
+        const float bwd = pk_of(w, 0, nc - 1) / w.lam_unif;
+        log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         break;
     }
     case 2: {  // data-driven birth in the window
@@ -323,24 +351,24 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         a.detv = __shfl_sync(MPP_FULL, dv, col);
         pn[0] = p0 / s0; pn[1] = p1 / s1; pn[2] = p2 / s2;
         dm[0] = mark_energy_f32(m, 0, p0); dm[1] = mark_energy_f32(m, 1, p1); dm[2] = mark_energy_f32(m, 2, p2);
-        const float fwd = pk_of(c.k, 2, nc) * dens_of(c, a.detv, pn[0], pn[1], pn[2]) / ((float)c.k.intensity * q_data);
-        const float bwd = pk_of(c.k, 3, nc + 1) / (float)(nc + 1);
-        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        const float fwd = pk_of(w, 2, nc) * dens_of(w, a.detv, pn[0], pn[1], pn[2]) / w.lam_data;
+        const float bwd = pk_of(w, 3, nc + 1) / (float)(nc + 1);
+        log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
     }
     case 3: {  // data-driven death
         if (!(w.win_mass > 0.0)) { valid = false; break; }
-        const float fwd = pk_of(c.k, 3, nc) / (float)nc;
-        const float bwd = pk_of(c.k, 2, nc - 1) * dens_of(c, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]) / ((float)c.k.intensity * q_data);
-        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        const float fwd = pk_of(w, 3, nc) / (float)nc;
+        const float bwd = pk_of(w, 2, nc - 1) * dens_of(w, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]) / w.lam_data;
+        log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         break;
     }
     case 4: {  // gaussian translation (symmetric: the proposal densities cancel)
-        double d0, d1;
-        box_muller(q0.z, q0.w, q1.x, q1.y, &d0, &d1);
-        const int nx_ = min(max((int)((double)w.x[r] + d0 * c.k.trl_sigma), 0), c.H - 1);
-        const int ny_ = min(max((int)((double)w.y[r] + d1 * c.k.trl_sigma), 0), c.W - 1);
+        float d0, d1;
+        box_muller_f(q0.z, q0.w, &d0, &d1);
+        const int nx_ = min(max((int)((float)w.x[r] + d0 * (float)c.k.trl_sigma), 0), c.H - 1);
+        const int ny_ = min(max((int)((float)w.y[r] + d1 * (float)c.k.trl_sigma), 0), c.W - 1);
         if (nx_ < w.x0 || nx_ >= w.x1 || ny_ < w.y0 || ny_ >= w.y1) { valid = false; break; }
         a.x = nx_; a.y = ny_; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
@@ -368,7 +396,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
         const float tot_e = warp_sum(rb);
         const float fwd = a.detv / tot_s, bwd = w.detv[r] / tot_e;  // p_kernel / n cancel
-        log_ratio = logf(bwd + W2_EPS) - logf(fwd + W2_EPS);
+        log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
     }
@@ -380,9 +408,9 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         R nv;
         const int ocls = cls_of(w.cls[r], pid);
         if (kernel == 6) {
-            double d0, d1;
-            box_muller(q0.w, q1.x, q1.y, q1.z, &d0, &d1);
-            nv = (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r])) + (R)(d0 * c.k.trf_sigma[pid]);
+            float d0, d1;
+            box_muller_f(q0.w, q1.x, &d0, &d1);
+            nv = (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r])) + (R)(d0 * (float)c.k.trf_sigma[pid]);
             const R vmax = (R)mark_vmax(pid);
             if (pid == 2) { nv = nv - r_floor(nv / vmax) * vmax; if (!(nv < vmax) || nv < 0) nv = 0; }
             else nv = r_min(r_max(nv, (R)0), vmax);
@@ -392,7 +420,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             ncls = warp_pick(v, u01f(q0.w), lane, &s);
             nv = mark_edge<R>(pid, ncls);
             const float pf = __shfl_sync(MPP_FULL, v, ncls) / s, pb = __shfl_sync(MPP_FULL, v, ocls) / s;
-            log_ratio = logf(pb + W2_EPS) - logf(pf + W2_EPS);  // p_kernel / n cancel
+            log_ratio = __logf(pb + W2_EPS) - __logf(pf + W2_EPS);  // p_kernel / n cancel
         }
         const float pnew = __shfl_sync(MPP_FULL, v, ncls);
         a.x = w.x[r]; a.y = w.y[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
@@ -425,9 +453,9 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (r >= 0 && w.handle[r] != MPP_NO_OBJECT && (int)(w.handle[r] >> 5) == w.ccell[ci]) dmk &= ~(1u << (w.handle[r] & 31));
         if (dmk == 0xffffffffu) { e->has_add = false; return; }
     }
-    const R de = delta_staged(m, w, r, e->has_add, a, lane, sx, sy);
+    const R de = delta_staged(m, w, r, e->has_add, a, lane, sx, sy, po, pa);
 #ifndef MPP_TRACE
-    if (dbg_maxdiff) {
+    if (DBG && dbg_maxdiff) {
         const R db = delta_brute(m, w, r, e->has_add, a, lane, sx, sy);
         const float diff = fabsf((float)(de - db));
         if (lane == 0) atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
@@ -435,35 +463,23 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
 #endif
     const float la = -(float)de / temp + log_ratio;
     e->evaluated = true;
-    e->accept = logf(u01f(q1.w) + W2_EPS) < la;
-#ifdef MPP_TRACE
-    if (dbg_maxdiff && lane == 0) {
-        float *tr = dbg_maxdiff + 8;
-        const int slot = atomicAdd(reinterpret_cast<int *>(dbg_maxdiff + 1), 1);
-        if (slot < 4000) {
-            float *o = tr + slot * 10;
-            o[0] = (float)win_id; o[1] = (float)it; o[2] = (float)kernel; o[3] = (float)r; o[4] = (float)de; o[5] = la;
-            o[6] = logf(u01f(q1.w) + W2_EPS); o[7] = e->accept ? 1.f : 0.f; o[8] = (float)nc; o[9] = log_ratio;
-        }
-    }
-#endif
+    e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
+
 }
 
-// Applies an accepted proposal to the staged state and to the storage cells (executed by one warp).
+// Applies an accepted proposal to the staged state and writes the new record (executed by the warp that evaluated it:
+// its po / pa scratch still holds the pair values between every staged entry and the added object).  The occupancy
+// masks of the window's storage cells are only published at the end of the visit.
 template <typename R>
-__device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy) {
+__device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy, const R *po, const R *pa) {
     const ModelDev &m = c.m;
     const int r = e.r;
-    int rx = 0, ry = 0;
-    if (r >= 0) {
-        rx = w.x[r]; ry = w.y[r];
-        if (lane == 0) {
-            w.flags[r] = 0;
-            const uint32_t h = w.handle[r];
-            for (int q = 0; q < 4; ++q)
-                if (w.ccell[q] == (int)(h >> 5)) { w.cmask[q] &= ~(1u << (h & 31)); __stcg(c.mask + w.ccell[q], w.cmask[q]); }
-            w.n_win -= 1; w.dn -= 1;
-        }
+    if (r >= 0 && lane == 0) {
+        w.flags[r] = 0;
+        const uint32_t h = w.handle[r];
+        for (int q = 0; q < 4; ++q)
+            if (w.ccell[q] == (int)(h >> 5)) w.cmask[q] &= ~(1u << (h & 31));
+        w.n_win -= 1; w.dn -= 1; w.masks_dirty = 1;
     }
     int s = -1;
     if (e.has_add) {
@@ -485,58 +501,94 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
             const uint32_t h = (uint32_t)w.ccell[ci] * 32u + slot;
             w.x[s] = a.x; w.y[s] = a.y; w.cls[s] = a.cls; w.handle[s] = h; w.uid[s] = w.uid_base + (uint32_t)it;
             w.size[s] = a.size; w.ratio[s] = a.ratio; w.angle[s] = a.angle;
-            w.hl[s] = a.hl; w.hw[s] = a.hw; w.ca[s] = a.ca; w.sa[s] = a.sa;
+            w.hl[s] = a.hl; w.hw[s] = a.hw; w.ca[s] = a.ca; w.sa[s] = a.sa; w.rad[s] = r_sqrt(a.hl * a.hl + a.hw * a.hw);
             w.pos[s] = a.pos; w.dm0[s] = a.dm0; w.dm1[s] = a.dm1; w.dm2[s] = a.dm2;
             shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &w.tm0[s], &w.tm1[s], &w.tm2[s]);
             w.detv[s] = a.detv; w.pn0[s] = a.pn0; w.pn1[s] = a.pn1; w.pn2[s] = a.pn2;
             w.flags[s] = W2_ALIVE | W2_WIN | W2_INNER;
-            w.n_win += 1; w.dn += 1;
+            w.n_win += 1; w.dn += 1; w.masks_dirty = 1;
             Rec<R> rec;
             rec.x = a.x; rec.y = a.y; rec.cls = a.cls; rec.uid = w.uid[s];
             rec.size = a.size; rec.ratio = a.ratio; rec.angle = a.angle;
             rec.e_pos = a.pos; rec.e_m[0] = w.tm0[s]; rec.e_m[1] = w.tm1[s]; rec.e_m[2] = w.tm2[s];
             rec.hl = a.hl; rec.hw = a.hw; rec.ca = a.ca; rec.sa = a.sa; rec.pad = 0;
             store_rec(c.recs + h, rec);
-            __threadfence();  // a concurrent window staging this cell must never see the mask bit before the record
             w.cmask[ci] |= 1u << slot;
-            __stcg(c.mask + w.ccell[ci], w.cmask[ci]);
         }
     }
     __syncwarp();
-    // refresh the reductions of everything within reach of the change (and of the new object)
+    // reductions: incremental for the addition (pair values are in po / pa); entries whose best partner was the
+    // removed object are rescanned; the new object's own top-2 is the top-2 of po / pa
     const int n = w.n;
+    R n_o1 = 0, n_o2 = 0, n_a1 = 0, n_a2 = 0;
+    int n_ao = -1, n_aa = -1, n_ao2 = -1, n_aa2 = -1;
     for (int k = lane; k < n; k += 32) {
-        if (!(w.flags[k] & W2_ALIVE) || !(w.flags[k] & W2_INNER)) continue;
-        bool need = k == s;
-        if (r >= 0) { const int dx = w.x[k] - rx, dy = w.y[k] - ry; need |= dx * dx + dy * dy <= m.max_d2; }
-        if (s >= 0) { const int dx = w.x[k] - w.x[s], dy = w.y[k] - w.y[s]; need |= dx * dx + dy * dy <= m.max_d2; }
-        if (need) recompute_top2(m, w, k, sx, sy);
+        if (k == s || !(w.flags[k] & W2_ALIVE)) continue;
+        // the removed object was this entry's best or second-best partner: its top-2 must be rescanned
+        const bool redo_ov = r >= 0 && (w.aov[k] == r || w.aov2[k] == r), redo_al = r >= 0 && (w.aal[k] == r || w.aal2[k] == r);
+        if (s >= 0) {
+            const R o = po[k], al = pa[k];
+            if (o > n_o1) { n_o2 = n_o1; n_ao2 = n_ao; n_o1 = o; n_ao = k; } else if (o > n_o2) { n_o2 = o; n_ao2 = k; }
+            if (al > n_a1) { n_a2 = n_a1; n_aa2 = n_aa; n_a1 = al; n_aa = k; } else if (al > n_a2) { n_a2 = al; n_aa2 = k; }
+            if (!redo_ov && (w.flags[k] & W2_INNER)) {
+                if (o > w.ov1[k]) { w.ov2[k] = w.ov1[k]; w.aov2[k] = w.aov[k]; w.ov1[k] = o; w.aov[k] = (short)s; }
+                else if (o > w.ov2[k]) { w.ov2[k] = o; w.aov2[k] = (short)s; }
+            }
+            if (!redo_al && (w.flags[k] & W2_INNER)) {
+                if (al > w.al1[k]) { w.al2[k] = w.al1[k]; w.aal2[k] = w.aal[k]; w.al1[k] = al; w.aal[k] = (short)s; }
+                else if (al > w.al2[k]) { w.al2[k] = al; w.aal2[k] = (short)s; }
+            }
+        }
+        if ((redo_ov || redo_al) && (w.flags[k] & W2_INNER)) recompute_top2(m, w, k, redo_ov, redo_al, sx, sy);
+    }
+    if (s >= 0) {  // merge the per-lane top-2 of (po, pa) into the new object's reductions (ties: lowest lane first)
+        const R mo = warp_max(n_o1);
+        const int lo = __ffs(__ballot_sync(MPP_FULL, n_o1 == mo)) - 1;
+        const R co = lane == lo ? n_o2 : n_o1;
+        const R so = warp_max(co);
+        const int lo2 = __ffs(__ballot_sync(MPP_FULL, co == so)) - 1;
+        const int ao = __shfl_sync(MPP_FULL, n_ao, lo);
+        const int ao2 = __shfl_sync(MPP_FULL, lane == lo ? n_ao2 : n_ao, lo2);
+        const R ma = warp_max(n_a1);
+        const int la = __ffs(__ballot_sync(MPP_FULL, n_a1 == ma)) - 1;
+        const R ca2 = lane == la ? n_a2 : n_a1;
+        const R sa2 = warp_max(ca2);
+        const int la2 = __ffs(__ballot_sync(MPP_FULL, ca2 == sa2)) - 1;
+        const int aa = __shfl_sync(MPP_FULL, n_aa, la);
+        const int aa2 = __shfl_sync(MPP_FULL, lane == la ? n_aa2 : n_aa, la2);
+        if (lane == 0) {
+            w.ov1[s] = mo; w.ov2[s] = so; w.aov[s] = (short)(mo > (R)0 ? ao : -1); w.aov2[s] = (short)(so > (R)0 ? ao2 : -1);
+            w.al1[s] = ma; w.al2[s] = sa2; w.aal[s] = (short)(ma > (R)0 ? aa : -1); w.aal2[s] = (short)(sa2 > (R)0 ? aa2 : -1);
+        }
     }
     __syncwarp();
 }
 
-template <typename R, int NW>
+template <typename R, int NW, bool DBG>
 __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp,
                                                    uint64_t seed, uint64_t sweep_id, uint32_t uid_base, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
     WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
-    R *clip = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+    R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R *sx = clip + (size_t)warp * (2 * 2 * 9 * 32) + lane, *sy = sx + 2 * 9 * 32;
+    constexpr int PER_WARP = 2 * 2 * 9 * 32 + 2 * W2_K;  // clip ping-pong buffers + pair-value stash
+    R *sx = scratch + (size_t)warp * PER_WARP + lane, *sy = sx + 2 * 9 * 32;
+    R *po = scratch + (size_t)warp * PER_WARP + 2 * 2 * 9 * 32, *pa = po + W2_K;
     const int a = blockIdx.x;
     if (a >= n_wi * n_wj) return;
     const int wi = ci + 3 * (a / n_wj), wj = cj + 3 * (a % n_wj);
     const uint32_t win_id = (uint32_t)wi * 65536u + (uint32_t)wj;
     const ModelDev &m = c.m;
+    const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
+    const int x0 = max(px0, 0), x1 = min(px0 + 32, c.H), y0 = max(py0, 0), y1 = min(py0 + 32, c.W);
 
-    // ------------------------------------------------------------------ staging (warp 0)
+    // ------------------------------------------------------------------ staging
+    // phase A (warp 0): window constants; handles / position keys of the objects within 64 px of the window
     if (warp == 0) {
-        const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
-        const int x0 = max(px0, 0), x1 = min(px0 + 32, c.H), y0 = max(py0, 0), y1 = min(py0 + 32, c.W);
         if (lane == 0) {
             w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
             w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
-            w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0;
+            w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0; w.masks_dirty = 0;
             w.uid_base = uid_base + (uint32_t)a * (uint32_t)per_visit;
             for (int q = 0; q < 4; ++q) {
                 const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
@@ -544,18 +596,19 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
                 w.ccell[q] = ok ? cy + cx * c.ny : -1;
                 w.cmask[q] = ok ? __ldcg(c.mask + cy + cx * c.ny) : 0xffffffffu;
             }
+            for (int k = 0; k < 8; ++k) w.pkf[k] = (float)c.k.p[k];
+            w.pk_e0 = (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])); w.pk_e2 = (float)(c.k.p[2] / (c.k.p[0] + c.k.p[2]));
+            w.dens_scale = (float)c.H * (float)c.W * 32768.0f / c.det_sum;
+            w.lam_unif = (float)(c.k.intensity * ((double)(x1 - x0) * (double)(y1 - y0)) / ((double)c.H * (double)c.W));
         }
-        // detection mass of the window rows
-        {
+        {   // detection mass of the window rows
             const size_t pitch = (size_t)c.W + 1;
             double rm = 0.0;
             if (lane < x1 - x0) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
             w.row_mass[lane] = (float)rm;
             const double tot = warp_sum(rm);
-            if (lane == 0) w.win_mass = tot;
+            if (lane == 0) { w.win_mass = tot; w.lam_data = (float)(c.k.intensity * tot / c.cell_cdf[c.ncell - 1]); }
         }
-        // objects of the storage cells covering [x0-64, x1+64) x [y0-64, y1+64).
-        // Phase A: collect (handle, position key, uid) of the objects inside that box (16-byte record heads only).
         const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
         const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
         int n = 0;
@@ -586,51 +639,49 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
             }
         }
         if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
-        __syncwarp();
-        // Phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
-        for (int k = lane; k < n; k += 32) {
-            const int key = w.x[k];
-            const uint32_t u = w.uid[k];
-            int rank = 0;
-            for (int v = 0; v < n; ++v) {
-                const int kv = w.x[v];
-                rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
-            }
-            w.order[rank] = w.handle[k];
-        }
-        __syncwarp();
-        // Phase C: one lane per object loads its full record
-        for (int p = lane; p < n; p += 32) {
-            const uint32_t h = w.order[p];
-            const Rec<R> rec = load_rec(c.recs + h);
-            const bool inw = rec.x >= x0 && rec.x < x1 && rec.y >= y0 && rec.y < y1;
-            const bool inner = rec.x >= x0 - 32 && rec.x < x1 + 32 && rec.y >= y0 - 32 && rec.y < y1 + 32;
-            w.x[p] = rec.x; w.y[p] = rec.y; w.cls[p] = rec.cls; w.handle[p] = h; w.uid[p] = rec.uid;
-            w.size[p] = rec.size; w.ratio[p] = rec.ratio; w.angle[p] = rec.angle;
-            w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa;
-            w.pos[p] = rec.e_pos; w.tm0[p] = rec.e_m[0]; w.tm1[p] = rec.e_m[1]; w.tm2[p] = rec.e_m[2];
-            w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
-        }
-        __syncwarp();
-        if (lane == 0) w.n = n;
-        // per-mark details of the window objects (needed by deaths, translations and mark transforms)
-        int nwin = 0;
-        for (int k = 0; k < n; ++k) {
-            if (!(w.flags[k] & W2_WIN)) continue;
-            ++nwin;
-            float detv, pn[3], dm[3];
-            pixel_info(c, w.x[k], w.y[k], w.cls[k], lane, &detv, pn, dm);
-            if (lane == 0) {
-                w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
-                w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
-            }
-        }
-        if (lane == 0) w.n_win = nwin;
-        __syncwarp();
-        // partner reductions of everything a move in the window can affect
-        for (int k = lane; k < n; k += 32)
-            if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, sx, sy);
+        if (lane == 0) { w.n = n; w.n_win = 0; }
     }
+    __syncthreads();
+    const int n0 = w.n;
+    // phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
+    for (int k = threadIdx.x; k < n0; k += 32 * NW) {
+        const int key = w.x[k];
+        const uint32_t u = w.uid[k];
+        int rank = 0;
+        for (int v = 0; v < n0; ++v) {
+            const int kv = w.x[v];
+            rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
+        }
+        w.order[rank] = w.handle[k];
+    }
+    __syncthreads();
+    // phase C: one thread per object loads its full record
+    for (int p = threadIdx.x; p < n0; p += 32 * NW) {
+        const uint32_t h = w.order[p];
+        const Rec<R> rec = load_rec(c.recs + h);
+        const bool inw = rec.x >= x0 && rec.x < x1 && rec.y >= y0 && rec.y < y1;
+        const bool inner = rec.x >= x0 - 32 && rec.x < x1 + 32 && rec.y >= y0 - 32 && rec.y < y1 + 32;
+        w.x[p] = rec.x; w.y[p] = rec.y; w.cls[p] = rec.cls; w.handle[p] = h; w.uid[p] = rec.uid;
+        w.size[p] = rec.size; w.ratio[p] = rec.ratio; w.angle[p] = rec.angle;
+        w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa; w.rad[p] = r_sqrt(rec.hl * rec.hl + rec.hw * rec.hw);
+        w.pos[p] = rec.e_pos; w.tm0[p] = rec.e_m[0]; w.tm1[p] = rec.e_m[1]; w.tm2[p] = rec.e_m[2];
+        w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
+        if (inw) atomicAdd(&w.n_win, 1);
+    }
+    __syncthreads();
+    // phase D: per-mark details of the window objects (deaths, translations, mark transforms), one warp per object;
+    // phase E: partner reductions of everything a move in the window can affect, one thread per object
+    for (int k = warp; k < n0; k += NW) {
+        if (!(w.flags[k] & W2_WIN)) continue;
+        float detv, pn[3], dm[3];
+        pixel_info(c, w.x[k], w.y[k], w.cls[k], lane, &detv, pn, dm);
+        if (lane == 0) {
+            w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
+            w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
+        }
+    }
+    for (int k = threadIdx.x; k < n0; k += 32 * NW)
+        if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, true, true, sx, sy);
     __syncthreads();
 
     // ------------------------------------------------------------------ speculative proposal rounds
@@ -638,7 +689,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
     while (it < per_visit) {
         Eval<R> e;
         const int mine = it + warp;
-        if (mine < per_visit) evaluate_proposal(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, &e, dbg_maxdiff);
+        if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff);
         else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; }
         if (lane == 0) { w.res_accept[warp] = e.accept ? 1 : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
         __syncthreads();
@@ -654,12 +705,16 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
                 if (!e.has_add && e.r >= 0) w.n_death += 1;
             }
             if (w.n >= W2_K && e.has_add && e.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
-            else commit_proposal(c, w, e, mine, lane, sx, sy);
+            else commit_proposal(c, w, e, mine, lane, sx, sy, po, pa);
         }
         __syncthreads();
         it += used;
     }
     if (threadIdx.x == 0) {
+        if (w.masks_dirty) {
+            __threadfence();  // records before masks: a window staging these cells must never see a mask bit without its record
+            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(c.mask + w.ccell[q], w.cmask[q]);
+        }
         atomicAdd(c.counters + 0, (unsigned long long)w.n_done);
         atomicAdd(c.counters + 1, (unsigned long long)w.n_acc);
         atomicAdd(c.counters + 2, (unsigned long long)w.n_birth);

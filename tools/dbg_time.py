@@ -1,0 +1,35 @@
+import sys, os, ctypes as C
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from mpp_cnn_rs_object_detection_b200 import synth, _lib
+from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec
+size = 2048
+dev = torch.device("cuda", 0)
+objs, det, marks = synth.make_scene_torch(0, (size, size), 2600, dev)
+Cc, H = bench.CALIB_HRCM, bench.HRC
+spec = ModelSpec(setup="legacy", pos_threshold=Cc["detection_threshold"], remap_coefs=Cc["coefs"], remap_intercepts=Cc["intercepts"],
+                 min_area=Cc["min_area"], max_area=Cc["max_area"], combinator="hierarchical",
+                 comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
+for nw, pv in ((1, 8), (4, 16)):
+    eng = Engine((size, size), device=dev)
+    eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    eng.run_windows(3, pv, nw, t0=0.02, seed=1)
+    dbg = torch.zeros(8 + 4000 * 10, dtype=torch.float32, device=dev)
+    cnt = (C.c_ulonglong * 8)()
+    # one colour launch worth of CTAs is ~470; capture the first 4000 CTAs (about one sweep)
+    _lib.check(eng.lib.mpp_run_windows(eng.ctx, 1, pv, nw, 0.02, 1.0, 0.0, 1, 3, cnt, dbg.data_ptr()))
+    d = dbg.cpu().numpy()
+    n = min(4000, int(d[1:2].view(np.int32)[0]))
+    tr = d[8:8 + n * 10].reshape(n, 10)
+    ghz = 1.9
+    print(f"nw={nw} pv={pv}: CTAs {n}")
+    for name, col in (("staged n", 1), ("n_win", 2), ("staging us", 3), ("eval us", 4), ("commit us", 5), ("rounds", 6), ("acc", 7), ("total us", 9)):
+        v = tr[:, col] / (ghz * 1e3) if "us" in name else tr[:, col]
+        print(f"  {name:12s} mean {v.mean():8.2f}  p50 {np.median(v):8.2f}  p90 {np.percentile(v, 90):8.2f}  max {v.max():8.2f}")
+    tot = tr[:, 9] / (ghz * 1e3)
+    worst = tr[np.argsort(-tot)[:5]]
+    print("  worst CTAs (n, n_win, staging, eval, commit, rounds, acc, total us):")
+    for r in worst:
+        print("   ", int(r[1]), int(r[2]), round(r[3] / 1900, 1), round(r[4] / 1900, 1), round(r[5] / 1900, 1), int(r[6]), int(r[7]), round(r[9] / 1900, 1))
