@@ -14,7 +14,7 @@
 #pragma once
 #include "mpp_chain.cuh"
 
-#define W2_K 96          // staged objects per window (window +- 64 px)
+#define W2_K 128         // staged objects per window (window +- 64 px)
 #define W2_MAXW 8        // warps per window (speculation depth)
 #define W2_EPS 1e-16f
 
