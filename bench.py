@@ -6,13 +6,14 @@
 
 Workload (configs[2] of BASELINE.json): synthetic 2048x2048 DOTA-vehicle-like scene, ~2k oriented rectangles, hrcM
 energy model (legacy setup + hierarchical combinator with the shipped weights / calibration).  One *step* = one image's
-worth of sampling: `--sweeps` parallel colour sweeps, every 32-px cell performing `--per-visit` local proposals per
-sweep (defaults give 2.46 M proposals, the reference's own budget for a 2048^2 image: 81 patches x 30 257 steps).
+worth of sampling: `--sweeps` parallel colour sweeps, every 32-px window performing `--per-visit` local proposals per
+sweep (defaults give ~2.4 M proposals, the reference's own budget for a 2048^2 image: 81 patches x 30 257 steps).
 N > 1: every rank samples its own scene (independent images -> weak scaling, no data-path collective).
 
 `value`     : proposals/s with the maps already resident in HBM (CUDA events around K steps, max over ranks).
-`e2e`       : the same metric through the host-facing call: pinned host maps -> H2D -> cell masses -> initial
-              configuration -> sweeps -> D2H of the final configuration, all inside the timed region.
+`e2e`       : the same metric through the public entry point api.sample_rjmcmc(ImageWMaps on the HOST, ...): pinned
+              host maps -> H2D -> prefix sums -> naive initial configuration -> sweeps -> D2H of the final configuration
+              as Rectangle objects, all inside the timed region.
 `roofline`  : algorithmic bytes/proposal (recomputed with the run's K2 and acceptance) x proposals
               per k_sweep launch / mean launch duration, against the measured HBM peak of MEASURED_PEAKS.json.
 `cpu_baseline`: the oracle's sequential sampler on the host cores, reference decomposition (256^2 patches, one process
@@ -55,8 +56,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--n-rect", type=int, default=0, help="candidate rectangles (0: 2600 per 2048^2, scaled by area)")
-    ap.add_argument("--sweeps", type=int, default=36)
-    ap.add_argument("--per-visit", type=int, default=16)
+    ap.add_argument("--sweeps", type=int, default=18)
+    ap.add_argument("--per-visit", type=int, default=32)
     ap.add_argument("--warps", type=int, default=4, help="warps per window (speculation depth) of the window sampler")
     ap.add_argument("--sampler", default="windows", choices=["windows", "cells"],
                     help="windows: mpp_run_windows (production); cells: mpp_run_sweeps (first-generation aligned cells)")
@@ -293,44 +294,51 @@ def run_b200(args):
     n1 = len(eng)
     value = proposals / (ms * 1e-3)
 
-    # ---- e2e: host maps -> device -> sampler -> host configuration
+    # ---- e2e: the public entry point api.sample_rjmcmc on HOST inputs (pinned maps), H2D and D2H inside the timed region
     e2e = None
     if not args.no_e2e:
+        import mpp_cnn_rs_object_detection_b200.api as api
         det_h = torch.empty(det.shape, dtype=torch.float32, pin_memory=True).copy_(det)
         marks_h = torch.empty(marks.shape, dtype=torch.float32, pin_memory=True).copy_(marks)
-        det_d, marks_d = torch.empty_like(det), torch.empty_like(marks)
-        xy_h = np.ascontiguousarray(objs[:, :2].astype(np.int32))
-        mk_h = np.ascontiguousarray(objs[:, 2:5])
-        d2h = 0
+        image = api.ImageWMaps(name=f"synthetic_{rank}", shape=(h, w), image=None, detection_map=det_h,
+                               param_dist_maps=[marks_h[0], marks_h[1], marks_h[2]], mappings=api.default_mappings(),
+                               param_names=["size", "ratio", "angle"])
+        setup = api.LegacyEnergySetup(calibration_params={}, energy_calibration=api.LegacyEnergiesCalibration(
+            CALIB_HRCM["detection_threshold"], list(CALIB_HRCM["coefs"]), list(CALIB_HRCM["intercepts"]), CALIB_HRCM["min_area"],
+            CALIB_HRCM["max_area"]))
+        comb = api.HierarchicalEnergyCombinator(np.array(HRC["weights_data"]), np.array(HRC["weights_prior"]),
+                                                np.array(HRC["data_prior_weights"]), HRC["detection_threshold"], HRC["bias"])
+        ncell = ((h + 31) // 32) * ((w + 31) // 32)
+        budget = args.sweeps * ncell * args.per_visit  # proposals per image, as in the device-resident steps
+        e2e_rng = np.random.default_rng(args.seed + 100 + rank)
+        tot = {"evaluated": 0, "launches": 0, "objects": 0}
 
-        def e2e_step(seed_off):
-            nonlocal d2h
-            det_d.copy_(det_h, non_blocking=True)
-            marks_d.copy_(marks_h, non_blocking=True)
-            eng.clear()
-            eng.set_maps(det_d, marks_d)
-            eng.add_objects(xy_h, mk_h)
-            run(args.sweeps, seed_off)
-            hd, xy, mk, uid = eng.read_objects()
-            d2h = hd.nbytes + xy.nbytes + mk.nbytes + uid.nbytes
+        def e2e_step():
+            out, st = api.sample_rjmcmc(image_data=image, rng=e2e_rng, num_samples=1, energy_combinator=comb, init_config="naive",
+                                        init_temperature=args.temperature, alpha_t=1.0, burn_in=budget - 3, energy_setup=setup,
+                                        samples_interval=1, target_temperature=0.0, proposals_per_visit=args.per_visit,
+                                        warps_per_window=args.warps, reuse_device_maps=False, return_stats=True)
+            rects = list(out[0])  # D2H of the final configuration -> List[Rectangle]
+            tot["evaluated"] += st["evaluated"]; tot["launches"] += st["launches"]; tot["objects"] = len(rects)
 
         e2e_steps = max(1, min(args.steps, 3))
-        e2e_step(1000)
-        run(0, 0, read_counters=True)
+        e2e_step()
+        tot.update(evaluated=0, launches=0)
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(e2e_steps):
-            e2e_step(2000 + s)
+            e2e_step()
         torch.cuda.synchronize()
         t_e2e = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        cnt2 = run(0, 0, read_counters=True)
-        p2 = sum_over_ranks(float(cnt2[4]))
-        e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4 + xy_h.nbytes + mk_h.nbytes + 4 * len(xy_h)),
-               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
-               "timer": "host wall clock around H2D + sampler + D2H, max over ranks"}
-        del det_h, marks_h, det_d, marks_d
+        p2 = sum_over_ranks(float(tot["evaluated"]))
+        e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4),
+               "d2h_bytes_per_step": int(tot["objects"] * (4 + 8 + 24 + 4)), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
+               "objects_found": tot["objects"], "gpu_launches": int(tot["launches"]),
+               "call": "api.sample_rjmcmc(ImageWMaps with pinned host maps, init_config='naive', fixed T) -> List[Rectangle]",
+               "timer": "host wall clock around the call (H2D + naive init + sampler + D2H), max over ranks"}
+        del det_h, marks_h, image
 
     # ---- roofline of the dominant kernel (k_sweep)
     ncell = ((h + 31) // 32) * ((w + 31) // 32)

@@ -35,38 +35,43 @@ def _evict(key):
     _MAPS_CACHE.pop(key, None)
 
 
-def device_maps(det, marks: Sequence, device=None) -> DeviceMaps:
-    """Uploads (once per set of source arrays) the maps to the device.  Tensors already on the device are used in place."""
+def device_maps(det, marks: Sequence, device=None, reuse: bool = True) -> DeviceMaps:
+    """Uploads the maps to the device (once per set of source arrays when reuse=True).  Tensors already on the device are
+    used in place; pinned host tensors are copied asynchronously on the current stream."""
     stacked = isinstance(marks, torch.Tensor) and marks.dim() == 4
     key = (id(det), id(marks)) if stacked else (id(det),) + tuple(id(m) for m in marks)
-    hit = _MAPS_CACHE.get(key)
+    hit = _MAPS_CACHE.get(key) if reuse else None
     if hit is not None:
         return hit
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if isinstance(det, torch.Tensor):
-        d = det.to(device=dev, dtype=torch.float32).contiguous()
+        d = det.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         det_sum = None
     else:
         det_np = np.ascontiguousarray(det, dtype=np.float32)
         det_sum = float(np.sum(det_np))  # shape_samplers.py:87 normalises with numpy's float32 sum
         d = torch.as_tensor(det_np).to(dev)
     if stacked:
-        mk = marks.to(device=dev, dtype=torch.float32).contiguous()
+        mk = marks.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
     else:
         if len(marks) != 3:
             raise ValueError("expected three (H,W,32) mark maps")
-        ms = [m.to(device=dev, dtype=torch.float32).contiguous() if isinstance(m, torch.Tensor)
-              else torch.as_tensor(np.ascontiguousarray(m, dtype=np.float32)).to(dev) for m in marks]
-        if any(m.dim() != 3 or m.shape[-1] != 32 for m in ms):
+        ts = [m if isinstance(m, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(m, dtype=np.float32)) for m in marks]
+        if any(t.dim() != 3 or t.shape[-1] != 32 or t.shape != ts[0].shape for t in ts):
             raise ValueError("expected three (H,W,32) mark maps")
-        nb = ms[0].numel() * 4
-        same_storage = all(m.untyped_storage().data_ptr() == ms[0].untyped_storage().data_ptr() for m in ms)
-        if same_storage and ms[1].data_ptr() == ms[0].data_ptr() + nb and ms[2].data_ptr() == ms[0].data_ptr() + 2 * nb:
-            h, w, k = ms[0].shape  # three consecutive slices of one (3,H,W,32) tensor: no copy
-            mk = torch.as_strided(ms[0], (3, h, w, k), (h * w * k, w * k, k, 1))
+        h, w, k = ts[0].shape
+        nb = ts[0].numel() * ts[0].element_size()
+        on_dev = all(t.is_cuda and t.device == dev and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+        if on_dev and all(t.untyped_storage().data_ptr() == ts[0].untyped_storage().data_ptr() for t in ts) and \
+                ts[1].data_ptr() == ts[0].data_ptr() + nb and ts[2].data_ptr() == ts[0].data_ptr() + 2 * nb:
+            mk = torch.as_strided(ts[0], (3, h, w, k), (h * w * k, w * k, k, 1))  # consecutive slices of one device tensor: no copy
         else:
-            mk = torch.stack(ms).contiguous()
+            mk = torch.empty((3, h, w, k), dtype=torch.float32, device=dev)
+            for i in range(3):  # one H2D (or D2D) copy per map straight into its slice: no staging copy
+                mk[i].copy_(ts[i], non_blocking=True)
     out = DeviceMaps(d, mk, det_sum)
+    if not reuse:
+        return out
     _MAPS_CACHE[key] = out
     try:
         weakref.finalize(det, _evict, key)
@@ -212,14 +217,14 @@ def apply_combinator(layout: TermLayout, combinator) -> ModelSpec:
 class DeviceState:
     """One device context plus the identity mirror of the Python objects stored in it."""
 
-    def __init__(self, support_shape: Tuple[int, int], layout: TermLayout, precision: str = "fp32", device=None):
+    def __init__(self, support_shape: Tuple[int, int], layout: TermLayout, precision: str = "fp32", device=None, reuse_maps: bool = True):
         self.support_shape = (int(support_shape[0]), int(support_shape[1]))
         self.layout = layout
         self.precision = precision
         self.engine = Engine(self.support_shape, device=device, precision=precision)
         self.maps: Optional[DeviceMaps] = None
         if layout.det is not None:
-            self.maps = device_maps(layout.det, layout.marks, self.engine.device)
+            self.maps = device_maps(layout.det, layout.marks, self.engine.device, reuse=reuse_maps)
             assert tuple(self.maps.det.shape) == self.support_shape, "detection map shape != support shape"
             self.engine.set_maps(self.maps.det, self.maps.marks, det_sum=self.maps.det_sum)
         self._comb_key = None

@@ -203,18 +203,22 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                   init_config: Union[str, List[Rectangle], None], init_temperature: float, alpha_t: Union[float, str], burn_in: int,
                   energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
                   iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
-                  proposals_per_visit: int = 8, colour_stride: int = 3, precision: str = "fp32"):
+                  proposals_per_visit: int = 32, warps_per_window: int = 4, precision: str = "fp32",
+                  reuse_device_maps: bool = True, return_stats: bool = False):
     """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
 
-    sampler='parallel'   colour-sweep sampler: max_iter + 1 proposals in total, spread over ceil(.. / (cells * per_visit))
-                         sweeps; the temperature follows the reference's geometric schedule as a function of the number of
-                         proposals made (one multiplication by alpha_t ** proposals_per_sweep per sweep).
-    sampler='sequential' the reference's one-proposal-at-a-time chain, run on the device."""
+    sampler='parallel'   window sampler (mpp_run_windows): max_iter + 1 proposals in total, spread over
+                         ceil(.. / (windows * proposals_per_visit)) sweeps; the temperature follows the reference's geometric
+                         schedule as a function of the number of proposals made (one multiplication by
+                         alpha_t ** proposals_per_sweep per sweep).
+    sampler='sequential' the reference's one-proposal-at-a-time chain, run on the device.
+    reuse_device_maps    False: always upload the maps (no cache keyed on the host arrays).
+    return_stats         True: returns (result, dict of device counters) instead of result."""
     if use_split_merge:
         raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
     unit_energies, pair_energies = energy_setup.make_energies(image_data)
     points = EPointsSet(points=[], support_shape=image_data.shape, unit_energies_constructors=unit_energies,
-                        pair_energies_constructors=pair_energies, precision=precision)
+                        pair_energies_constructors=pair_energies, precision=precision, reuse_device_maps=reuse_device_maps)
     st = points._state
     if isinstance(init_config, str) and init_config == "gt":
         st.add_many(image_data.gt_config)
@@ -249,6 +253,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         eng = st.engine
         ncell = ((image_data.shape[0] + 31) // 32) * ((image_data.shape[1] + 31) // 32)
         per_sweep = ncell * int(proposals_per_visit)
+        stats = {"proposals": 0, "accepted": 0, "births": 0, "deaths": 0, "evaluated": 0, "sweeps": 0}
         seed = int(rng.integers(0, 2 ** 62))
         # snapshot steps of the reference's sampling_rule, expressed in sweeps
         snap_steps = [s for s in range(burn_in, max_iter + 1) if s % samples_interval == 0] if samples_interval > 0 else []
@@ -259,8 +264,9 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         for stop in snap_sweeps + ([total_sweeps] if (not snap_sweeps or snap_sweeps[-1] < total_sweeps) else []):
             n = stop - done
             if n > 0:
-                eng.run_sweeps(n, proposals_per_visit, colour_stride, t0=temp, alpha_t=alpha_sweep, t_target=float(target_temperature),
-                               seed=seed, sweep_offset=done, read_counters=False)
+                eng.run_windows(n, proposals_per_visit, warps_per_window, t0=temp, alpha_t=alpha_sweep,
+                                t_target=float(target_temperature), seed=seed, sweep_offset=done, read_counters=False)
+                stats["sweeps"] += n
                 for _ in range(n):
                     if temp > target_temperature:
                         temp *= alpha_sweep
@@ -269,6 +275,9 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                 st.refresh_from_device()
                 points.energy_graph._members = dict.fromkeys(st.handle_of)
                 states.append(points.copy())
+        if return_stats:
+            c = eng.run_windows(0, proposals_per_visit, warps_per_window, t0=max(temp, 1e-30))
+            stats.update(proposals=c[0], accepted=c[1], births=c[2], deaths=c[3], evaluated=c[4])
         st.refresh_from_device()
         points.energy_graph._members = dict.fromkeys(st.handle_of)
         if not states:
@@ -277,6 +286,11 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
     else:
         raise ValueError(f"sampler must be 'parallel' or 'sequential', got {sampler!r}")
     end = time.perf_counter()
+    if return_stats:
+        if sampler != "parallel":
+            stats = {"proposals": max_iter + 1, "evaluated": max_iter + 1}
+        stats["launches"] = st.engine.launches
+        result = (result, stats)
     logging.info(f"rjmcmc on image {image_data.name} ran in {end - start:.2f}s ({(end - start) / max(1, max_iter):.1e}s/iter) "
                  f"(int. {intensity} | iter {max_iter} | num_samples {num_samples} | {sampler})")
     return result
