@@ -58,9 +58,11 @@ def parse_args():
     ap.add_argument("--n-rect", type=int, default=0, help="candidate rectangles (0: 2600 per 2048^2, scaled by area)")
     ap.add_argument("--sweeps", type=int, default=18)
     ap.add_argument("--per-visit", type=int, default=32)
-    ap.add_argument("--warps", type=int, default=4, help="warps per window (speculation depth) of the window sampler")
+    ap.add_argument("--warps", type=int, default=8, help="warps per window (speculation depth) of the window sampler")
     ap.add_argument("--sampler", default="windows", choices=["windows", "cells"],
                     help="windows: mpp_run_windows (production); cells: mpp_run_sweeps (first-generation aligned cells)")
+    ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "colours"],
+                    help="window sampler: one persistent dataflow kernel per call, or one launch per colour class")
     ap.add_argument("--stride", type=int, default=3)
     ap.add_argument("--temperature", type=float, default=0.02)
     ap.add_argument("--seed", type=int, default=0)
@@ -260,7 +262,7 @@ def run_b200(args):
     def run(n_sweeps, seed_off, read_counters=False):
         if args.sampler == "windows":
             return eng.run_windows(n_sweeps, args.per_visit, args.warps, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
-                                   sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
+                                   sweep_offset=seed_off * args.sweeps, read_counters=read_counters, schedule=args.schedule)
         return eng.run_sweeps(n_sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
                               sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
 
@@ -346,9 +348,12 @@ def run_b200(args):
     acc = accepted / max(1.0, proposals)
     bpp = bytes_per_proposal(k2, acc, h, w, kernel_probabilities())
     peak, peak_src = measured_peak()
-    sweep_launches = args.steps * args.sweeps * (9 if args.sampler == "windows" else args.stride * args.stride)
+    if args.sampler == "windows" and args.schedule == "dataflow":
+        sweep_launches = args.steps  # one persistent kernel per step
+    else:
+        sweep_launches = args.steps * args.sweeps * (9 if args.sampler == "windows" else args.stride * args.stride)
     achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep2<float,%d>" % args.warps if args.sampler == "windows" else "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": ("k_windows_dataflow<float,%d>" % args.warps if args.schedule == "dataflow" else "k_sweep2<float,%d>" % args.warps) if args.sampler == "windows" else "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
                 "proposals_per_launch": proposals / world / sweep_launches, "us_per_launch": 1e3 * ms / sweep_launches,
                 "note": "latency/parallelism-bound Markov chain: see DESIGN.md"}
@@ -357,7 +362,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "sampler": args.sampler, "sweeps_per_step": args.sweeps,
-                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "colour_stride": 3 if args.sampler == "windows" else args.stride,
+                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "schedule": args.schedule if args.sampler == "windows" else "colours", "colour_stride": 3 if args.sampler == "windows" else args.stride,
                        "attempted_per_step": attempted / args.steps,
                        "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated (empty perturbations and moves leaving their window are not counted)", "objects_start": n0, "objects_end": n1, "acceptance": acc,
                        "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU",

@@ -235,10 +235,13 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
  * evaluate consecutive proposals speculatively (the chain does not depend on n_warps).  The kernel mixture is the
  * reference's when a window holds objects and births-only when it is empty.  debug_maxdiff (device float, may be
  * NULL): every Delta-energy is also recomputed by brute force and the largest |difference| is written there.
+ * schedule 0: one launch per colour class (9 per sweep, a device-wide barrier between colours).  schedule 1: one
+ * persistent kernel for the whole call; window visits are claimed in (sweep, colour, window) order and each starts as soon
+ * as the earlier visits within 64 px of it have completed (dataflow; same chain as schedule 0, bit for bit).
  * counters_host as in mpp_run_sweeps. */
-int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, double t0, double alpha_t,
-                    double t_target, uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host,
-                    float *debug_maxdiff);
+int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, int schedule, double t0,
+                    double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
+                    unsigned long long *counters_host, float *debug_maxdiff);
 
 /* Draws n pixels from the normalised detection map (sample_point_2d, utils/sampler2d.py:39-46, as used by
  * RectangleSampler.sample shape_samplers.py:90-94) and their three mark classes (shape_samplers.py:113-117):

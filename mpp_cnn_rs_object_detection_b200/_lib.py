@@ -97,7 +97,7 @@ def load():
     lib.mpp_run_chain.argtypes = [vp, i32, f64, f64, f64, u64, u64, vp, C.POINTER(C.c_ulonglong)]
     lib.mpp_sample_proposals.argtypes = [vp, vp, i32, u64, u64, vp]
     lib.mpp_proposal_probs.argtypes = [vp, vp, i32, vp]
-    lib.mpp_run_windows.argtypes = [vp, i32, i32, i32, f64, f64, f64, u64, u64, C.POINTER(C.c_ulonglong), vp]
+    lib.mpp_run_windows.argtypes = [vp, i32, i32, i32, i32, f64, f64, f64, u64, u64, C.POINTER(C.c_ulonglong), vp]
     lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")

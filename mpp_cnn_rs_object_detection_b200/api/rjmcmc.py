@@ -203,7 +203,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                   init_config: Union[str, List[Rectangle], None], init_temperature: float, alpha_t: Union[float, str], burn_in: int,
                   energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
                   iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
-                  proposals_per_visit: int = 32, warps_per_window: int = 4, precision: str = "fp32",
+                  proposals_per_visit: int = 32, warps_per_window: int = 8, precision: str = "fp32",
                   reuse_device_maps: bool = True, return_stats: bool = False):
     """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
 

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -38,6 +39,9 @@ struct mpp_ctx {
     ModelDev m;
     KernDev k;
     int *h_pinned = nullptr;            // small pinned read-back area (16 x 8 bytes)
+    void *d_plan = nullptr;             // device scratch of the dataflow schedule (offsets, temperatures, completion grids)
+    size_t plan_bytes = 0;
+    int num_sms = 0;
     uint32_t window_uid_next = 0x80000000u;  // uids of objects born in mpp_run_windows: host-tracked, upper half of the uid space
 };
 
@@ -855,6 +859,7 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, 128));
+    CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_recs, 0, rec * (size_t)h->ncell * MPP_CELL_CAPACITY, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
@@ -883,7 +888,7 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
-    cudaFree(h->d_rowcount); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
+    cudaFree(h->d_rowcount); cudaFree(h->d_plan); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
     return MPP_OK;
@@ -1277,14 +1282,86 @@ static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj,
     return cudaGetLastError();
 }
 
-extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_warps, double t0, double alpha_t, double t_target,
+template <typename R, int NW, bool DBG>
+static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, double alpha_t, double t_target, uint64_t seed,
+                           uint64_t sweep_offset, float *dbg) {
+    const int S = n_sweeps;
+    const int dg = (std::max(h->H, h->W) + 31) / 32 + 2;
+    std::vector<int> ints((size_t)3 * S + 2);
+    std::vector<float> temps(S);
+    int *ox = ints.data(), *oy = ox + S, *base = oy + S;
+    double temp = t0;
+    int total = 0;
+    for (int s = 0; s < S; ++s) {
+        const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_offset + (uint64_t)s));
+        ox[s] = (int)(hsh & 31); oy[s] = (int)((hsh >> 5) & 31);
+        base[s] = total;
+        total += ((h->H + ox[s] + 31) / 32) * ((h->W + oy[s] + 31) / 32);
+        temps[s] = (float)temp;
+        if (temp > t_target) temp *= alpha_t;
+    }
+    base[S] = total;
+    // device layout: [ints: ox, oy, task_base | next_task | done 2*dg*dg] [floats: temp]
+    const size_t n_int = (size_t)3 * S + 2 + 1 + (size_t)2 * dg * dg;
+    const size_t bytes = n_int * sizeof(int) + (size_t)S * sizeof(float);
+    if (bytes > h->plan_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_plan);
+        h->d_plan = nullptr; h->plan_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->d_plan, bytes * 2));
+        h->plan_bytes = bytes * 2;
+    }
+    int *d_int = reinterpret_cast<int *>(h->d_plan);
+    float *d_temp = reinterpret_cast<float *>(d_int + n_int);
+    CUDA_TRY(cudaMemsetAsync(d_int + (size_t)3 * S + 2, 0, (1 + (size_t)2 * dg * dg) * sizeof(int), h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_int, ints.data(), ((size_t)3 * S + 2) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_temp, temps.data(), (size_t)S * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+    SweepPlan plan;
+    plan.n_sweeps = S; plan.total_tasks = total; plan.dg = dg;
+    plan.ox = d_int; plan.oy = d_int + S; plan.task_base = d_int + 2 * S;
+    plan.next_task = d_int + 3 * S + 2; plan.done = d_int + 3 * S + 3; plan.temp = d_temp;
+    const uint32_t uid_base = h->window_uid_next;
+    h->window_uid_next += (uint32_t)total * (uint32_t)per_visit;
+    if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        CUDA_TRY(cudaFuncSetAttribute(k_windows_dataflow<R, NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_windows_dataflow<R, NW, DBG>, 32 * NW, smem));
+        if (blocks_per_sm < 1) return fail(MPP_ERR_CUDA, "k_windows_dataflow does not fit on an SM");
+    }
+    const int grid = std::min(total, blocks_per_sm * h->num_sms);  // all CTAs co-resident: the in-order task queue needs it
+    k_windows_dataflow<R, NW, DBG><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_warps, int schedule, double t0, double alpha_t, double t_target,
                                uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host, float *debug_maxdiff) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_windows: set maps, model and kernels first");
     if (n_sweeps < 0 || per_visit < 1 || per_visit > 64 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 64)");
     if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 1, 2, 4 or 8");
+    if (schedule != 0 && schedule != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows: schedule must be 0 (colour barriers) or 1 (dataflow)");
     if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
     if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_windows: the window sampler is float32 only (use mpp_run_chain / mpp_replay for float64)");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (schedule == 1 && n_sweeps > 0) {
+        int rc;
+#define MPP_LAUNCH_D(NWV) (debug_maxdiff \
+        ? launch_dataflow<float, NWV, true>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff) \
+        : launch_dataflow<float, NWV, false>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff))
+        switch (n_warps) {
+        case 1: rc = MPP_LAUNCH_D(1); break;
+        case 2: rc = MPP_LAUNCH_D(2); break;
+        case 4: rc = MPP_LAUNCH_D(4); break;
+        default: rc = MPP_LAUNCH_D(8); break;
+        }
+#undef MPP_LAUNCH_D
+        if (rc != MPP_OK) return rc;
+        if (counters_host) return read_counters(h, counters_host);
+        return MPP_OK;
+    }
     double temp = t0;
     for (int s = 0; s < n_sweeps; ++s) {
         const uint64_t sweep_id = sweep_offset + (uint64_t)s;

@@ -564,19 +564,15 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
     __syncwarp();
 }
 
+// One visit of window (wi, wj) of the grid shifted by (ox, oy): staging, `per_visit` proposals, publication.
+// `uid_first` is the uid of the first object this visit may create.  Must be called by the whole CTA.
 template <typename R, int NW, bool DBG>
-__global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp,
-                                                   uint64_t seed, uint64_t sweep_id, uint32_t uid_base, float *dbg_maxdiff) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
-    R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+__device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi, int wj, int ox, int oy, int per_visit, float temp,
+                             uint64_t seed, uint64_t sweep_id, uint32_t uid_first, float *dbg_maxdiff) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int PER_WARP = 2 * 2 * 9 * 32 + 2 * W2_K;  // clip ping-pong buffers + pair-value stash
     R *sx = scratch + (size_t)warp * PER_WARP + lane, *sy = sx + 2 * 9 * 32;
     R *po = scratch + (size_t)warp * PER_WARP + 2 * 2 * 9 * 32, *pa = po + W2_K;
-    const int a = blockIdx.x;
-    if (a >= n_wi * n_wj) return;
-    const int wi = ci + 3 * (a / n_wj), wj = cj + 3 * (a % n_wj);
     const uint32_t win_id = (uint32_t)wi * 65536u + (uint32_t)wj;
     const ModelDev &m = c.m;
     const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
@@ -589,7 +585,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
             w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
             w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
             w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0; w.masks_dirty = 0;
-            w.uid_base = uid_base + (uint32_t)a * (uint32_t)per_visit;
+            w.uid_base = uid_first;
             for (int q = 0; q < 4; ++q) {
                 const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
                 const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);
@@ -721,5 +717,107 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
         atomicAdd(c.counters + 3, (unsigned long long)w.n_death);
         atomicAdd(c.counters + 4, (unsigned long long)w.n_eval);
         if (w.dn) atomicAdd(c.n_objects, w.dn);
+    }
+}
+
+// ---- schedule 0: one launch per colour class (global barrier between colours) ------------------------
+template <typename R, int NW, bool DBG>
+__global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp,
+                                                   uint64_t seed, uint64_t sweep_id, uint32_t uid_base, float *dbg_maxdiff) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
+    R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+    const int a = blockIdx.x;
+    if (a >= n_wi * n_wj) return;
+    window_visit<R, NW, DBG>(c, w, scratch, ci + 3 * (a / n_wj), cj + 3 * (a % n_wj), ox, oy, per_visit, temp, seed, sweep_id,
+                             uid_base + (uint32_t)a * (uint32_t)per_visit, dbg_maxdiff);
+}
+
+// ---- schedule 1: persistent dataflow kernel -------------------------------------------------------------
+// All visits of all sweeps of one mpp_run_windows call are numbered in the order (sweep, colour, window) and claimed
+// in that order from a global counter by a grid of co-resident CTAs.  A visit starts as soon as every EARLIER visit
+// whose window lies within 64 px of its own has completed (same sweep: neighbours of earlier colours; previous sweep:
+// every window of the previous grid within 64 px; older sweeps follow by transitivity because each grid tiles the
+// image).  Dependencies always have smaller numbers, hence are already claimed by a running CTA: no deadlock.  There
+// is no global barrier between colours or sweeps, so slow windows no longer hold the other SMs idle.
+struct SweepPlan {
+    int n_sweeps, total_tasks, dg;   // dg: pitch of the completion grids
+    const int *ox, *oy;              // [n_sweeps] grid offsets
+    const float *temp;               // [n_sweeps]
+    const int *task_base;            // [n_sweeps + 1]
+    int *done;                       // [2][dg][dg]: (local sweep index + 1) of the last completed visit, by sweep parity
+    int *next_task;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename R, int NW, bool DBG>
+__global__ void __launch_bounds__(32 * NW) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
+                                                             uint32_t uid_base, float *dbg_maxdiff) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
+    R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+    __shared__ int s_task;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);
+        __syncthreads();
+        const int t = s_task;
+        if (t >= plan.total_tasks) break;
+        // decode (sweep, colour, window)
+        int lo = 0, hi = plan.n_sweeps - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (plan.task_base[mid] <= t) lo = mid; else hi = mid - 1; }
+        const int s = lo;
+        const int ox = plan.ox[s], oy = plan.oy[s];
+        const int nwx = (c.H + ox + 31) / 32, nwy = (c.W + oy + 31) / 32;
+        int local = t - plan.task_base[s], col = 0, n_wj = 1;
+        for (; col < 9; ++col) {
+            const int ci = col / 3, cj = col % 3;
+            const int a_i = ci < nwx ? (nwx - ci + 2) / 3 : 0, a_j = cj < nwy ? (nwy - cj + 2) / 3 : 0;
+            if (local < a_i * a_j) { n_wj = a_j; break; }
+            local -= a_i * a_j;
+        }
+        const int wi = col / 3 + 3 * (local / n_wj), wj = col % 3 + 3 * (local % n_wj);
+        // wait for the conflicting earlier visits
+        if (warp == 0) {
+            int *done_cur = plan.done + (size_t)(s & 1) * plan.dg * plan.dg, *done_prev = plan.done + (size_t)((s + 1) & 1) * plan.dg * plan.dg;
+            const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
+            const int x0 = max(px0, 0), x1 = min(px0 + 32, c.H), y0 = max(py0, 0), y1 = min(py0 + 32, c.W);
+            int pi0 = 0, pi1 = -1, pj0 = 0, pj1 = -1;
+            if (s > 0) {
+                const int oxp = plan.ox[s - 1], oyp = plan.oy[s - 1];
+                const int nwxp = (c.H + oxp + 31) / 32, nwyp = (c.W + oyp + 31) / 32;
+                pi0 = max((max(x0 - 64, 0) + oxp) >> 5, 0); pi1 = min((min(x1 - 1 + 64, c.H - 1) + oxp) >> 5, nwxp - 1);
+                pj0 = max((max(y0 - 64, 0) + oyp) >> 5, 0); pj1 = min((min(y1 - 1 + 64, c.W - 1) + oyp) >> 5, nwyp - 1);
+            }
+            const int pw = pj1 - pj0 + 1, pn = (pi1 - pi0 + 1) * pw;
+            for (;;) {
+                bool ok = true;
+                if (lane < 25) {  // same sweep, earlier colours, |dwi|, |dwj| <= 2
+                    const int ni = wi + lane / 5 - 2, nj = wj + lane % 5 - 2;
+                    if (ni >= 0 && nj >= 0 && ni < nwx && nj < nwy && (ni % 3) * 3 + nj % 3 < col)
+                        ok = ld_acquire(done_cur + ni * plan.dg + nj) >= s + 1;
+                }
+                for (int q = lane; q < pn; q += 32)  // every window of the previous sweep within 64 px
+                    ok = ok && ld_acquire(done_prev + (pi0 + q / pw) * plan.dg + pj0 + q % pw) >= s;
+                if (__all_sync(MPP_FULL, ok)) break;
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        window_visit<R, NW, DBG>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
+                                 uid_base + (uint32_t)t * (uint32_t)per_visit, dbg_maxdiff);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_release(plan.done + (size_t)(s & 1) * plan.dg * plan.dg + wi * plan.dg + wj, s + 1);
+        }
     }
 }

@@ -328,17 +328,19 @@ class Engine:
         self.launches += int(n_sweeps) * stride * stride
         return [int(v) for v in cnt] if read_counters else None
 
-    def run_windows(self, n_sweeps: int, proposals_per_visit: int = 16, n_warps: int = 4, t0: float = 1.0, alpha_t: float = 1.0,
-                    t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True, debug: bool = False):
+    def run_windows(self, n_sweeps: int, proposals_per_visit: int = 32, n_warps: int = 8, t0: float = 1.0, alpha_t: float = 1.0,
+                    t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True, debug: bool = False,
+                    schedule: str = "dataflow"):
         """Production parallel sampler (mpp_run_windows): shifted 32-px windows, shared-memory resident visits, speculative
         evaluation by `n_warps` warps.  Returns [proposals, accepted, births, deaths, evaluated, 0, 0, 0] (+ the largest
         |fast - brute-force| Delta-energy difference when debug=True)."""
         cnt = (C.c_ulonglong * 8)()
         dbg = torch.zeros(1, dtype=torch.float32, device=self.device) if debug else None
-        _lib.check(self.lib.mpp_run_windows(self.ctx, int(n_sweeps), int(proposals_per_visit), int(n_warps), float(t0), float(alpha_t),
+        sched = {"colours": 0, "dataflow": 1}[schedule]
+        _lib.check(self.lib.mpp_run_windows(self.ctx, int(n_sweeps), int(proposals_per_visit), int(n_warps), sched, float(t0), float(alpha_t),
                                             float(t_target), int(seed), int(sweep_offset), cnt if read_counters else None,
                                             None if dbg is None else dbg.data_ptr()))
-        self.launches += int(n_sweeps) * 9
+        self.launches += (1 if n_sweeps > 0 else 0) if sched == 1 else int(n_sweeps) * 9
         out = [int(v) for v in cnt] if read_counters else None
         if debug:
             return out, float(dbg.cpu().item())

@@ -22,17 +22,18 @@ def _scene(cfg, seed=5, shape=(192, 224), n_rect=60):
 def test_fast_delta_equals_brute_force(cfg, n_rect, temp):
     """n_rect=170 on 192x224 is ~4x the benchmark density: many partners within reach, overlaps and second-best partners."""
     objs, det, marks, eng = _scene(cfg, n_rect=n_rect)
-    cnt, maxdiff = eng.run_windows(40, proposals_per_visit=12, n_warps=4, t0=temp, seed=3, debug=True)
+    cnt, maxdiff = eng.run_windows(40, proposals_per_visit=12, n_warps=4, t0=temp, seed=3, debug=True, schedule="colours" if n_rect < 100 else "dataflow")
     assert cnt[0] > 0 and cnt[4] > 0 and cnt[1] > 0
     assert maxdiff < 2e-5, maxdiff
     assert len(eng) == len(objs) + cnt[2] - cnt[3]
 
 
-def test_chain_is_independent_of_speculation_depth():
+def test_chain_is_independent_of_speculation_depth_and_schedule():
+    """The chain depends neither on the number of speculating warps nor on the schedule (colour barriers vs dataflow)."""
     finals = []
-    for nw in (1, 2, 4, 8):
+    for nw, schedule in ((1, "colours"), (2, "colours"), (4, "colours"), (8, "colours"), (1, "dataflow"), (4, "dataflow"), (8, "dataflow")):
         objs, det, marks, eng = _scene("legacy")
-        cnt = eng.run_windows(25, proposals_per_visit=10, n_warps=nw, t0=0.03, seed=9)
+        cnt = eng.run_windows(25, proposals_per_visit=10, n_warps=nw, t0=0.03, seed=9, schedule=schedule)
         h, xy, mk, uid = eng.read_objects()
         order = np.lexsort((xy[:, 1], xy[:, 0]))
         finals.append((cnt[:5], xy[order], mk[order]))
