@@ -140,6 +140,10 @@ int mpp_abi_struct_size(int which);
  * a uniform grid of 32-px cells over a (height, width) support.  `stream` is a cudaStream_t (0 = default). */
 int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precision, void *stream);
 int mpp_ctx_destroy(mpp_ctx *ctx);
+/* Returns a context to its freshly created state (no objects, no maps / model / kernels, counters and uid source
+ * reset) and rebinds it to `stream`, keeping its device allocations: contexts are pooled by the host layer because
+ * allocating and freeing the index per image costs tens of milliseconds. */
+int mpp_ctx_reset(mpp_ctx *ctx, void *stream);
 
 /* ImageWMaps.detection_map (H,W) f32 and param_dist_maps 3x(H,W,32) f32 (custom_types/image_w_maps.py:12-22).
  * det_sum <= 0: the library reduces the map itself (float64); otherwise the caller passes

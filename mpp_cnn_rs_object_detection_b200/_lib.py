@@ -48,7 +48,7 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_num_objects", "mpp_read_objects", "mpp_energy_vectors", "mpp_delta_batch", "mpp_replay",
            "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
-           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows"]
+           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset"]
 
 _lib = None
 
@@ -75,6 +75,7 @@ def load():
     lib.mpp_abi_struct_size.argtypes = [i32]
     lib.mpp_ctx_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, vp]
     lib.mpp_ctx_destroy.argtypes = [vp]
+    lib.mpp_ctx_reset.argtypes = [vp, vp]
     lib.mpp_set_maps.argtypes = [vp, vp, vp, f64]
     lib.mpp_set_model.argtypes = [vp, C.POINTER(ModelParams)]
     lib.mpp_set_kernels.argtypes = [vp, C.POINTER(KernelParams)]

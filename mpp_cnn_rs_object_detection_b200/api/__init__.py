@@ -13,5 +13,5 @@ from .kernels import (BirthKernel, DataDrivenShapeTransformKernel, DataDrivenTra
                       GaussianShapeTransformKernel, GaussianTranslationKernel, Kernel, make_kernels)
 from .mappings import ValueMapping, default_mappings, output_vector_to_value  # noqa: F401
 from .point_set import PointsSet  # noqa: F401
-from .rjmcmc import RJMCMC, StopOnMaxIter, naive_detection, nms_distance, sample_rjmcmc  # noqa: F401
+from .rjmcmc import RJMCMC, StopOnMaxIter, naive_detection, nms_distance, sample_rjmcmc, sample_rjmcmc_batch  # noqa: F401
 from .shapes import Point, Rectangle, polygon_to_abw, rect_to_poly, rotation_matrix, sra_to_wla, wla_to_sra  # noqa: F401

@@ -29,6 +29,23 @@ class DeviceMaps:
 
 
 _MAPS_CACHE: Dict[Tuple[int, ...], DeviceMaps] = {}
+# idle device buffers for uploads (reuse=False): (device index, H, W) -> [(det buffer, marks buffer)].  cudaMalloc /
+# cudaFree of a 1.6 GB map set costs far more than the upload itself, so the buffers are recycled.
+_UPLOAD_POOL: Dict[Tuple[int, int, int], list] = {}
+_UPLOAD_POOL_SIZE = 3
+
+
+def _upload_buffers(dev: torch.device, h: int, w: int):
+    idle = _UPLOAD_POOL.get((dev.index, h, w))
+    if idle:
+        return idle.pop()
+    return (torch.empty((h, w), dtype=torch.float32, device=dev), torch.empty((3, h, w, 32), dtype=torch.float32, device=dev))
+
+
+def _recycle(key, bufs):
+    idle = _UPLOAD_POOL.setdefault(key, [])
+    if len(idle) < _UPLOAD_POOL_SIZE:
+        idle.append(bufs)
 
 
 def _evict(key):
@@ -44,15 +61,34 @@ def device_maps(det, marks: Sequence, device=None, reuse: bool = True) -> Device
     if hit is not None:
         return hit
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    det_on_dev = isinstance(det, torch.Tensor) and det.is_cuda
+    pooled = None
+    if not reuse and not det_on_dev:
+        hh, ww = int(det.shape[0]), int(det.shape[1])
+        pooled = _upload_buffers(dev, hh, ww)
     if isinstance(det, torch.Tensor):
-        d = det.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         det_sum = None
+        if pooled is not None:
+            d = pooled[0]
+            d.copy_(det, non_blocking=True)
+        else:
+            d = det.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
     else:
         det_np = np.ascontiguousarray(det, dtype=np.float32)
         det_sum = float(np.sum(det_np))  # shape_samplers.py:87 normalises with numpy's float32 sum
-        d = torch.as_tensor(det_np).to(dev)
+        if pooled is not None:
+            d = pooled[0]
+            d.copy_(torch.as_tensor(det_np))
+        else:
+            d = torch.as_tensor(det_np).to(dev)
     if stacked:
-        mk = marks.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if pooled is not None and not marks.is_cuda:
+            mk = pooled[1]
+            mk.copy_(marks, non_blocking=True)
+        else:
+            mk = marks.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
     else:
         if len(marks) != 3:
             raise ValueError("expected three (H,W,32) mark maps")
@@ -66,10 +102,12 @@ def device_maps(det, marks: Sequence, device=None, reuse: bool = True) -> Device
                 ts[1].data_ptr() == ts[0].data_ptr() + nb and ts[2].data_ptr() == ts[0].data_ptr() + 2 * nb:
             mk = torch.as_strided(ts[0], (3, h, w, k), (h * w * k, w * k, k, 1))  # consecutive slices of one device tensor: no copy
         else:
-            mk = torch.empty((3, h, w, k), dtype=torch.float32, device=dev)
+            mk = pooled[1] if pooled is not None else torch.empty((3, h, w, k), dtype=torch.float32, device=dev)
             for i in range(3):  # one H2D (or D2D) copy per map straight into its slice: no staging copy
                 mk[i].copy_(ts[i], non_blocking=True)
     out = DeviceMaps(d, mk, det_sum)
+    if pooled is not None:
+        weakref.finalize(out, _recycle, (dev.index, int(d.shape[0]), int(d.shape[1])), pooled)
     if not reuse:
         return out
     _MAPS_CACHE[key] = out
@@ -217,14 +255,15 @@ def apply_combinator(layout: TermLayout, combinator) -> ModelSpec:
 class DeviceState:
     """One device context plus the identity mirror of the Python objects stored in it."""
 
-    def __init__(self, support_shape: Tuple[int, int], layout: TermLayout, precision: str = "fp32", device=None, reuse_maps: bool = True):
+    def __init__(self, support_shape: Tuple[int, int], layout: TermLayout, precision: str = "fp32", device=None, reuse_maps: bool = True,
+                 maps: Optional[DeviceMaps] = None):
         self.support_shape = (int(support_shape[0]), int(support_shape[1]))
         self.layout = layout
         self.precision = precision
         self.engine = Engine(self.support_shape, device=device, precision=precision)
         self.maps: Optional[DeviceMaps] = None
         if layout.det is not None:
-            self.maps = device_maps(layout.det, layout.marks, self.engine.device, reuse=reuse_maps)
+            self.maps = maps if maps is not None else device_maps(layout.det, layout.marks, self.engine.device, reuse=reuse_maps)
             assert tuple(self.maps.det.shape) == self.support_shape, "detection map shape != support shape"
             self.engine.set_maps(self.maps.det, self.maps.marks, det_sum=self.maps.det_sum)
         self._comb_key = None

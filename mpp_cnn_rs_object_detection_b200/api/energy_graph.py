@@ -5,6 +5,7 @@ The reference keeps Python lists of UnitEnergy / PairEnergy instances per object
 device cell lists, and `ue_per_point` / `pe_per_point` are read-only views built on demand from device queries."""
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Iterable, List, Optional, Set, Union
 
 import numpy as np
@@ -27,7 +28,11 @@ class _PerPointView:
     """dict-like view: `u in view`, `view[u]` -> list of UnitEnergy / PairEnergy, `.keys()`, `len(view)`."""
 
     def __init__(self, graph: "EnergyGraph", pair: bool):
-        self._g, self._pair = graph, pair
+        self._ref, self._pair = weakref.ref(graph), pair  # weak: no reference cycle, device state is released promptly
+
+    @property
+    def _g(self) -> "EnergyGraph":
+        return self._ref()
 
     def __contains__(self, u):
         return u in self._g._members

@@ -20,7 +20,7 @@ class EPointsSet:
     def __init__(self, points: Iterable[Point], support_shape: Tuple[int, int],
                  unit_energies_constructors: List[UnitEnergyConstructor],
                  pair_energies_constructors: List[PairEnergyConstructor], debug=False, precision: str = "fp32",
-                 _state: DeviceState = None, reuse_device_maps: bool = True):
+                 _state: DeviceState = None, reuse_device_maps: bool = True, _device_maps=None):
         self.debug = debug
         if len(pair_energies_constructors) > 0:  # energy_point_set.py:33-36
             self.maximum_interaction_radius = np.max([pec.max_dist for pec in pair_energies_constructors])
@@ -28,7 +28,7 @@ class EPointsSet:
             self.maximum_interaction_radius = 0
         if _state is None:
             layout = build_layout(unit_energies_constructors, pair_energies_constructors)  # asserts unique names (:25-29)
-            _state = DeviceState(support_shape, layout, precision=precision, reuse_maps=reuse_device_maps)
+            _state = DeviceState(support_shape, layout, precision=precision, reuse_maps=reuse_device_maps, maps=_device_maps)
             _state.add_many(list(points))
         self._state = _state
         self.points: PointsSet = PointsSet(support_shape=support_shape, maximum_interaction_radius=self.maximum_interaction_radius,

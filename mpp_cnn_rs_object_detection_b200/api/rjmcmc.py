@@ -204,7 +204,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                   energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
                   iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
                   proposals_per_visit: int = 32, warps_per_window: int = 8, precision: str = "fp32",
-                  reuse_device_maps: bool = True, return_stats: bool = False):
+                  reuse_device_maps: bool = True, return_stats: bool = False, _device_maps=None):
     """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
 
     sampler='parallel'   window sampler (mpp_run_windows): max_iter + 1 proposals in total, spread over
@@ -218,7 +218,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
     unit_energies, pair_energies = energy_setup.make_energies(image_data)
     points = EPointsSet(points=[], support_shape=image_data.shape, unit_energies_constructors=unit_energies,
-                        pair_energies_constructors=pair_energies, precision=precision, reuse_device_maps=reuse_device_maps)
+                        pair_energies_constructors=pair_energies, precision=precision, reuse_device_maps=reuse_device_maps,
+                        _device_maps=_device_maps)
     st = points._state
     if isinstance(init_config, str) and init_config == "gt":
         st.add_many(image_data.gt_config)
@@ -294,3 +295,57 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
     logging.info(f"rjmcmc on image {image_data.name} ran in {end - start:.2f}s ({(end - start) / max(1, max_iter):.1e}s/iter) "
                  f"(int. {intensity} | iter {max_iter} | num_samples {num_samples} | {sampler})")
     return result
+
+
+def sample_rjmcmc_batch(images, rng: np.random.Generator, with_scores: bool = False, **params):
+    """sample_rjmcmc over a sequence of images (the role of `_map_to_images(partial(sample_rjmcmc, ...), images)`,
+    models/mpp/train_energy_combination/train_utils.py:11-18 and mpp_model.py:250-264) with the host-to-device upload of
+    image i+1 overlapped with the sampling of image i (second CUDA stream, recycled device buffers).  `params` are
+    sample_rjmcmc's keyword arguments.  Device state is released image by image, so the result is detached: per image a
+    list (one entry per sample) of lists of Rectangle; with_scores=True returns (rectangles, Papangelou scores of the last
+    sample: exp(+Delta E of removal), mpp_model.py:296-304) per image; return_stats=True appends the counters dict."""
+    import torch
+
+    from .device_state import build_layout, device_maps
+    images = list(images)
+    if not images:
+        return []
+    energy_setup = params["energy_setup"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload(img):
+        unit, pair = energy_setup.make_energies(img)
+        layout = build_layout(unit, pair)
+        copy_stream.wait_stream(main)  # the buffers handed out by the pool may still be read by queued kernels
+        with torch.cuda.stream(copy_stream):
+            dm = device_maps(layout.det, layout.marks, dev, reuse=False)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dm, ev
+
+    results = []
+    nxt = upload(images[0])
+    for i, img in enumerate(images):
+        dm, ev = nxt
+        nxt = upload(images[i + 1]) if i + 1 < len(images) else None
+        main.wait_event(ev)
+        out = sample_rjmcmc(image_data=img, rng=rng, _device_maps=dm, **params)
+        stats = None
+        if params.get("return_stats"):
+            out, stats = out
+        rects = [list(ps) for ps in out]
+        item = rects
+        if with_scores:
+            st = out[-1]._state
+            st.use_combinator(params.get("energy_combinator"))
+            objs = st.objects()
+            rec = np.concatenate([st.proposal_record(u, None) for u in objs]) if objs else None
+            scores = np.exp(st.engine.delta_batch(rec)) if objs else np.zeros(0)
+            item = (rects, scores)
+        if stats is not None:
+            item = (item, stats)
+        results.append(item)
+        del out, dm  # releases the device context and the upload buffers to their pools
+    return results

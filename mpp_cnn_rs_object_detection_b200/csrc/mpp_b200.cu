@@ -894,6 +894,24 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     return MPP_OK;
 }
 
+int mpp_ctx_reset(mpp_ctx *h, void *stream) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_ctx_reset: null ctx");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_next_uid, 0, sizeof(uint32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
+    h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f;
+    h->maps_set = false; h->model_set = false; h->kernels_set = false;
+    h->window_uid_next = 0x80000000u;
+    memset(&h->m, 0, sizeof(h->m));
+    memset(&h->k, 0, sizeof(h->k));
+    return MPP_OK;
+}
+
 int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_sum) {
     if (!h || !det || !marks) return fail(MPP_ERR_INVALID, "mpp_set_maps: null argument");
     CUDA_TRY(cudaSetDevice(h->device));

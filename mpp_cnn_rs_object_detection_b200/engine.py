@@ -159,6 +159,9 @@ def snap_to_edges(marks: np.ndarray) -> np.ndarray:
 class Engine:
     """One mpp_ctx.  Not thread-safe; bound to one CUDA device and the current torch stream at creation."""
 
+    _POOL: dict = {}      # (device index, H, W, precision) -> idle contexts (device allocations kept)
+    POOL_SIZE = 4
+
     def __init__(self, shape: Tuple[int, int], device: Optional[torch.device] = None, precision: str = "fp32"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
@@ -169,10 +172,16 @@ class Engine:
         self.shape = (int(shape[0]), int(shape[1]))
         self.precision = precision
         self.stream = torch.cuda.current_stream(self.device)
-        ctx = C.c_void_p()
-        _lib.check(self.lib.mpp_ctx_create(C.byref(ctx), self.device.index, self.shape[0], self.shape[1],
-                                           _lib.PRECISION_FP64 if precision == "fp64" else _lib.PRECISION_FP32,
-                                           C.c_void_p(self.stream.cuda_stream)))
+        self._key = (self.device.index, self.shape[0], self.shape[1], precision)
+        idle = Engine._POOL.get(self._key)
+        if idle:
+            ctx = idle.pop()
+            _lib.check(self.lib.mpp_ctx_reset(ctx, C.c_void_p(self.stream.cuda_stream)))
+        else:
+            ctx = C.c_void_p()
+            _lib.check(self.lib.mpp_ctx_create(C.byref(ctx), self.device.index, self.shape[0], self.shape[1],
+                                               _lib.PRECISION_FP64 if precision == "fp64" else _lib.PRECISION_FP32,
+                                               C.c_void_p(self.stream.cuda_stream)))
         self.ctx = ctx
         self.model: Optional[ModelSpec] = None
         self._det = None
@@ -180,9 +189,23 @@ class Engine:
         self.launches = 0  # kernels launched through this engine (bench gpu_launches)
 
     def close(self):
-        if getattr(self, "ctx", None) is not None and self.ctx:
-            self.lib.mpp_ctx_destroy(self.ctx)
+        """Returns the context to the pool (its device buffers are reused by the next Engine of the same shape)."""
+        ctx = getattr(self, "ctx", None)
+        if ctx is not None and ctx:
             self.ctx = None
+            self._det = self._marks = None
+            idle = Engine._POOL.setdefault(self._key, [])
+            if len(idle) < Engine.POOL_SIZE:
+                idle.append(ctx)
+            else:
+                self.lib.mpp_ctx_destroy(ctx)
+
+    @classmethod
+    def drain_pool(cls):
+        lib = _lib.load()
+        for idle in cls._POOL.values():
+            while idle:
+                lib.mpp_ctx_destroy(idle.pop())
 
     def __del__(self):
         try:
