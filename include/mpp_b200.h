@@ -247,6 +247,16 @@ int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_w
                     double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
                     unsigned long long *counters_host, float *debug_maxdiff);
 
+/* One third of a sweep of the window sampler, restricted to a band of rows: the three colour launches (cj = 0, 1, 2) of
+ * the window rows wi = ci (mod 3) whose first pixel row lies in [row_lo, row_hi).  Window rows of equal ci are >= 65 px
+ * apart, so ranks that own disjoint row bands of one scene can run this concurrently and only need to exchange their
+ * boundary objects (mpp_pack_rows / mpp_unpack_rows) between two values of ci.  The grid offset, the random streams and
+ * the uids of born objects depend only on (seed, sweep_id, window): a split scene follows the same chain as
+ * mpp_run_windows(schedule 0) on one GPU.  mpp_window_grid returns the grid offset of a sweep. */
+int mpp_run_window_rows(mpp_ctx *ctx, int proposals_per_visit, int n_warps, double temperature, uint64_t seed,
+                        uint64_t sweep_id, int ci, int row_lo, int row_hi);
+int mpp_window_grid(mpp_ctx *ctx, uint64_t seed, uint64_t sweep_id, int *ox_host, int *oy_host);
+
 /* Draws n pixels from the normalised detection map (sample_point_2d, utils/sampler2d.py:39-46, as used by
  * RectangleSampler.sample shape_samplers.py:90-94) and their three mark classes (shape_samplers.py:113-117):
  * out [n][5] int32 = x, y, class_size, class_ratio, class_angle. */

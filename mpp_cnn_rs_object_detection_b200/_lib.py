@@ -48,7 +48,7 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_num_objects", "mpp_read_objects", "mpp_energy_vectors", "mpp_delta_batch", "mpp_replay",
            "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
-           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset"]
+           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid"]
 
 _lib = None
 
@@ -99,6 +99,8 @@ def load():
     lib.mpp_sample_proposals.argtypes = [vp, vp, i32, u64, u64, vp]
     lib.mpp_proposal_probs.argtypes = [vp, vp, i32, vp]
     lib.mpp_run_windows.argtypes = [vp, i32, i32, i32, i32, f64, f64, f64, u64, u64, C.POINTER(C.c_ulonglong), vp]
+    lib.mpp_run_window_rows.argtypes = [vp, i32, i32, f64, u64, u64, i32, i32, i32]
+    lib.mpp_window_grid.argtypes = [vp, u64, u64, C.POINTER(i32), C.POINTER(i32)]
     lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")

@@ -1409,6 +1409,46 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
     return MPP_OK;
 }
 
+extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, double temperature, uint64_t seed, uint64_t sweep_id, int ci,
+                                   int row_lo, int row_hi) {
+    NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_window_rows: set maps, model and kernels first");
+    if (per_visit < 1 || per_visit > 64 || !(temperature > 0.0) || ci < 0 || ci > 2 || row_lo > row_hi)
+        return fail(MPP_ERR_INVALID, "mpp_run_window_rows: bad arguments");
+    if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: n_warps must be 1, 2, 4 or 8");
+    if (h->m.setup == MPP_SETUP_TOY || h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_window_rows: float32 map-driven model only");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
+    const int ox = (int)(hsh & 31), oy = (int)((hsh >> 5) & 31);
+    const int nwx = (h->H + ox + 31) / 32, nwy = (h->W + oy + 31) / 32;
+    // window rows whose first pixel row max(32*wi - ox, 0) lies in [row_lo, row_hi) and wi = ci (mod 3)
+    int first = -1, count = 0;
+    for (int wi = ci; wi < nwx; wi += 3) {
+        const int start = std::max(32 * wi - ox, 0);
+        if (start >= row_lo && start < row_hi) { if (first < 0) first = wi; ++count; }
+    }
+    if (count == 0) return MPP_OK;
+    for (int cj = 0; cj < 3; ++cj) {
+        const int n_wj = cj < nwy ? (nwy - cj + 2) / 3 : 0;
+        if (n_wj == 0) continue;
+        cudaError_t e;
+        switch (n_warps) {
+        case 1: e = launch_sweep2<float, 1, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
+        case 2: e = launch_sweep2<float, 2, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
+        case 4: e = launch_sweep2<float, 4, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
+        default: e = launch_sweep2<float, 8, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
+        }
+        if (e != cudaSuccess) return fail(MPP_ERR_CUDA, std::string("k_sweep2 launch: ") + cudaGetErrorString(e));
+    }
+    return MPP_OK;
+}
+
+extern "C" int mpp_window_grid(mpp_ctx *h, uint64_t seed, uint64_t sweep_id, int *ox_host, int *oy_host) {
+    if (!h || !ox_host || !oy_host) return fail(MPP_ERR_INVALID, "mpp_window_grid: null argument");
+    const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
+    *ox_host = (int)(hsh & 31); *oy_host = (int)((hsh >> 5) & 31);
+    return MPP_OK;
+}
+
 extern "C" int mpp_run_chain(mpp_ctx *h, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed, uint64_t step_offset,
                   mpp_step_result *trace, unsigned long long *counters_host) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_chain: set maps, model and kernels first");

@@ -585,7 +585,9 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
             w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
             w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0; w.masks_dirty = 0;
-            w.uid_base = uid_first;
+            // uids of objects born here: a function of (sweep, window) only, so that the chain and the uids do not depend on
+            // the schedule or on how a scene is split across GPUs (wraps after 2^31 / (windows * per_visit) sweeps)
+            w.uid_base = 0x80000000u | (uint32_t)(((sweep_id * (uint64_t)((c.nx + 2) * (c.ny + 2)) + (uint64_t)(wi * (c.ny + 2) + wj)) * (uint64_t)per_visit) & 0x7fffffffull);
             for (int q = 0; q < 4; ++q) {
                 const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
                 const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);

@@ -369,6 +369,18 @@ class Engine:
             return out, float(dbg.cpu().item())
         return out
 
+    def run_window_rows(self, proposals_per_visit: int, n_warps: int, temperature: float, seed: int, sweep_id: int, ci: int,
+                        row_lo: int, row_hi: int):
+        """One third of a sweep (window rows wi = ci mod 3) restricted to the rows [row_lo, row_hi) (scene split across GPUs)."""
+        _lib.check(self.lib.mpp_run_window_rows(self.ctx, int(proposals_per_visit), int(n_warps), float(temperature), int(seed),
+                                                int(sweep_id), int(ci), int(row_lo), int(row_hi)))
+        self.launches += 3
+
+    def window_grid(self, seed: int, sweep_id: int):
+        ox, oy = C.c_int(), C.c_int()
+        _lib.check(self.lib.mpp_window_grid(self.ctx, int(seed), int(sweep_id), C.byref(ox), C.byref(oy)))
+        return ox.value, oy.value
+
     def run_chain(self, n_steps: int, t0: float = 1.0, alpha_t: float = 1.0, t_target: float = 0.0, seed: int = 0,
                   step_offset: int = 0, trace: bool = False, read_counters: bool = True):
         """Sequential device chain with the reference's global kernels (RJMCMC.run, rjmcmc.py:83-181)."""

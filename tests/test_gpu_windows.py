@@ -87,3 +87,37 @@ def test_stationary_distribution_matches_sequential_chain():
     mc, sc = _batch_se(nc)
     print(f"\nobject count at T={temp}: device chain {mb:.3f}+-{sb:.3f} | windows {mc:.3f}+-{sc:.3f}")
     assert abs(mb - mc) < 5 * np.hypot(sb, sc) + 0.04, (mb, mc)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_split_scene_follows_the_single_gpu_chain(world):
+    """A scene split into row bands (one device context per band, boundary objects exchanged between colour-row phases)
+    ends in exactly the configuration of mpp_run_windows(schedule='colours') on one context."""
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg, synth
+    from tests.gpu_util import make_engine
+    objs, det, marks = synth.make_scene(21, (352, 224), 110)
+    n_sweeps, pv, nw, temp, seed = 12, 8, 4, 0.03, 17
+    uid = np.arange(len(objs))
+    single = make_engine("legacy", det, marks, "fp32", intensity=max(1, len(objs)))
+    single.add_objects(objs[:, :2], objs[:, 2:5], uid=uid)
+    for s in range(n_sweeps):
+        single.run_windows(1, pv, nw, t0=temp, seed=seed, sweep_offset=s, schedule="colours", read_counters=False)
+        assert single.window_grid(seed, s) == mg.grid_offset(seed, s)
+    _, xy1, mk1, uid1 = single.read_objects()
+    scenes = []
+    for r in range(world):
+        eng = make_engine("legacy", det, marks, "fp32", intensity=max(1, len(objs)))
+        sc = mg.SplitScene(eng, det.shape[0], r, world, capacity=1024)
+        sel = sc.select_initial(objs[:, :2])
+        eng.add_objects(objs[sel, :2], objs[sel, 2:5], uid=uid[sel])
+        scenes.append(sc)
+    for s in range(n_sweeps):
+        mg.sweep_local(scenes, pv, nw, temp, seed, s)
+    parts = [sc.owned_objects() for sc in scenes]
+    xy2 = np.concatenate([p[0] for p in parts]); mk2 = np.concatenate([p[1] for p in parts]); uid2 = np.concatenate([p[2] for p in parts])
+    assert len(xy2) == len(xy1) and len(set(uid2.tolist())) == len(uid2)
+    o1, o2 = np.argsort(uid1), np.argsort(uid2)
+    np.testing.assert_array_equal(uid1[o1], uid2[o2])
+    np.testing.assert_array_equal(xy1[o1], xy2[o2])
+    np.testing.assert_array_equal(mk1[o1], mk2[o2])
+    assert abs(len(xy1) - len(objs)) < len(objs)  # the chain did something sensible
