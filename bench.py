@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--temperature", type=float, default=0.02)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=4000, help="proposals per CPU worker in the cpu_baseline sample")
+    ap.add_argument("--split", action="store_true",
+                    help="BASELINE configs[3]: ONE scene split into row bands across the ranks (halo exchange over NCCL between "
+                         "colour-row phases) instead of one independent scene per rank; strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -210,6 +213,93 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ product arm
+def run_split(args):
+    """One scene split across the ranks (BASELINE configs[3])."""
+    import torch
+    import torch.distributed as dist
+
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg, synth
+    from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    h = w = args.size
+    objs, det, marks = synth.make_scene_torch(args.seed, (h, w), n_rect_for(args), device)  # same scene on every rank
+    spec = ModelSpec(setup="legacy", pos_threshold=CALIB_HRCM["detection_threshold"], remap_coefs=CALIB_HRCM["coefs"],
+                     remap_intercepts=CALIB_HRCM["intercepts"], min_area=CALIB_HRCM["min_area"], max_area=CALIB_HRCM["max_area"],
+                     combinator="hierarchical",
+                     comb_w=list(HRC["weights_data"]) + list(HRC["weights_prior"]) + list(HRC["data_prior_weights"]) + [0.0],
+                     comb_bias=HRC["bias"], comb_threshold=HRC["detection_threshold"])
+    eng = Engine((h, w), device=device)
+    eng.set_maps(det, marks)
+    eng.set_model(spec)
+    eng.set_kernels(intensity=max(1, len(objs)))
+    scene = mg.SplitScene(eng, h, rank, world, capacity=16384)
+    sel = scene.select_initial(objs[:, :2])
+    eng.add_objects(objs[sel, :2], objs[sel, 2:5], uid=np.arange(len(objs))[sel])
+
+    def step(k):
+        for s in range(args.sweeps):
+            if world > 1:
+                mg.sweep_dist(scene, args.per_visit, args.warps, args.temperature, args.seed, k * args.sweeps + s)
+            else:
+                for ci in range(3):
+                    scene.compute(ci, args.per_visit, args.warps, args.temperature, args.seed, k * args.sweeps + s)
+
+    for k in range(args.warmup):
+        step(k)
+    eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)  # reset counters
+    launches0 = eng.launches
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    cnt = eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)
+    t = torch.tensor([ev0.elapsed_time(ev1), float(cnt[4]), float(cnt[0]), float(cnt[1]), float(len(scene.owned_objects()[0])),
+                      float(eng.launches - launches0)], dtype=torch.float64, device=device)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms = float(tmax[0])
+    proposals, attempted, accepted, n_end, launches = (float(v) for v in t[1:])
+    ncell = ((h + 31) // 32) * ((w + 31) // 32)
+    bpp = bytes_per_proposal(25.0 * n_end / ncell, accepted / max(1.0, proposals), h, w, __import__("mpp_cnn_rs_object_detection_b200.engine", fromlist=["x"]).kernel_probabilities())
+    peak, peak_src = measured_peak()
+    achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": proposals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args) + f", ONE scene split into {world} row band(s)", "sampler": "windows",
+                       "schedule": "colours (3 halo exchanges per sweep over NCCL send/recv)", "sweeps_per_step": args.sweeps,
+                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "objects_start": len(objs), "objects_end": n_end,
+                       "acceptance": accepted / max(1.0, proposals), "attempted_per_step": attempted / args.steps,
+                       "l2": "inputs larger than L2"},
+            "ms_per_image": ms / args.steps, "e2e": None, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_sweep2<float,%d>" % args.warps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp}}
+    eng.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -405,6 +495,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.split:
+        run_split(args)
     else:
         run_b200(args)
 
