@@ -316,3 +316,38 @@ def test_rjmcmc_step_and_run_and_sample_rjmcmc():
         assert all(isinstance(r, api.Rectangle) for r in final)
         # annealed from T=0.1 to ~0.005 (a T0=1 schedule needs the full 30k-step budget): the configuration is close to the objects the maps were synthesised from
         assert 0.5 * len(truth) <= len(final) <= 1.6 * len(truth), (sampler, len(final), len(truth))
+
+
+def test_mpp_model_infer_and_cli(tmp_path):
+    """MPPModel.infer (whole image and reference-style tiling + merge) and the command line on a synthetic scene."""
+    import json
+    import os
+    api = _api()
+    from mpp_cnn_rs_object_detection_b200 import synth
+    from mpp_cnn_rs_object_detection_b200.main import main as cli
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    cfg = json.load(open(os.path.join(gold, "model_mpp_hrcM", "config.json")))
+    cfg["inference"]["rjmcmc_params"].update(init_temperature=0.1, alpha_t=0.9996, burn_in=12000, samples_interval=64)
+    model = api.MPPModel(cfg, model_dir=os.path.join(gold, "model_mpp_hrcM"))
+    truth, det, marks = synth.make_scene(31, (300, 420), 110)
+    img = api.ImageWMaps("0007", det.shape, None, det, marks, api.default_mappings(), ["size", "ratio", "angle"])
+    found = {}
+    for tile in (False, True):
+        res = model.infer([img], results_dir=str(tmp_path / f"tile{int(tile)}"), tile=tile)[0]
+        centers = res["detection_center"]
+        assert len(res["detection_score"]) == len(centers) == len(res["detection"]) and res["detection"].shape[1:] == (4, 2)
+        d = np.abs(centers[:, None, :] - truth[None, :, :2]).max(-1)
+        recall = (d.min(0) <= 3).mean()
+        precision = (d.min(1) <= 3).mean()
+        assert recall > 0.85 and precision > 0.85, (tile, recall, precision, len(centers), len(truth))
+        assert os.path.exists(tmp_path / f"tile{int(tile)}" / "0007_results.pkl")
+        found[tile] = len(centers)
+        if tile:  # merge_patches: no two detections closer than 3 px survive
+            dd = np.abs(centers[:, None, :] - centers[None, :, :]).astype(float)
+            dist = np.hypot(dd[..., 0], dd[..., 1]) + np.eye(len(centers)) * 1e9
+            assert dist.min() > 3
+    assert abs(found[True] - found[False]) <= 0.2 * len(truth)
+    out = cli(["-p", "infer", "-m", "mpp", "-c", os.path.join(gold, "model_mpp_hrcM", "config.json"), "--synthetic", "128x160"])
+    assert len(out) == 1 and "detection_score" in out[0]
+    with pytest.raises(ValueError):
+        cli(["-p", "train", "-m", "mpp", "-c", os.path.join(gold, "model_mpp_hrcM", "config.json")])
