@@ -349,3 +349,66 @@ def sample_rjmcmc_batch(images, rng: np.random.Generator, with_scores: bool = Fa
         results.append(item)
         del out, dm  # releases the device context and the upload buffers to their pools
     return results
+
+
+def sample_rjmcmc_tiles(images, rng: np.random.Generator, n_streams: int = 8, **params):
+    """Independent chains on a batch of small tiles (BASELINE configs[4]: e.g. 256 tiles of 512x512), run concurrently on
+    `n_streams` CUDA streams so that their persistent kernels share the SMs (one 512^2 tile exposes only ~36 concurrently
+    active windows, far fewer than the GPU can hold).  Single-sample, parallel sampler only.  `params` as sample_rjmcmc
+    (init_config 'naive' / 'gt' / list / None).  Returns one list of Rectangle per tile."""
+    import torch
+    images = list(images)
+    if params.get("num_samples", 1) != 1 or params.get("sampler", "parallel") != "parallel":
+        raise ValueError("sample_rjmcmc_tiles runs one parallel-sampler chain per tile (num_samples=1)")
+    energy_setup, comb = params["energy_setup"], params["energy_combinator"]
+    init_config = params.get("init_config", "naive")
+    burn_in, interval = params["burn_in"], params["samples_interval"]
+    alpha_t, t0, t_target = params["alpha_t"], params["init_temperature"], params["target_temperature"]
+    mult = params.get("iter_multiplier")
+    if mult is not None:
+        burn_in, interval, alpha_t = burn_in * mult, interval * mult, np.power(alpha_t, 1 / mult)
+    if isinstance(alpha_t, str) and alpha_t == "auto":
+        alpha_t, t_target = np.power(t_target / t0, 1 / burn_in), 0
+    pv, nw = int(params.get("proposals_per_visit", 32)), int(params.get("warps_per_window", 8))
+    max_iter = int(burn_in) + 2 * int(interval)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(n_streams, len(images))))]
+    main = torch.cuda.current_stream(dev)
+    states = []
+    for i, img in enumerate(images):  # phase 1: upload, index, initial configuration (each tile on its stream)
+        s = streams[i % len(streams)]
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+            unit, pair = energy_setup.make_energies(img)
+            pts = EPointsSet([], img.shape, unit, pair, reuse_device_maps=params.get("reuse_device_maps", True))
+            st = pts._state
+            if isinstance(init_config, str) and init_config == "gt":
+                st.add_many(img.gt_config)
+            elif isinstance(init_config, str) and init_config == "naive":
+                st.engine.naive_init(float(energy_setup.detection_threshold), 6.0)
+            elif init_config is not None:
+                st.add_many(list(init_config))
+            n0 = len(st.engine)
+            st.use_kernels(max(1, n0), kernel_probabilities_default())
+            st.use_combinator(comb)
+            states.append((pts, s))
+    seeds = [int(rng.integers(0, 2 ** 62)) for _ in images]
+    for (pts, s), img, seed in zip(states, images, seeds):  # phase 2: every chain is launched before any result is read
+        ncell = ((img.shape[0] + 31) // 32) * ((img.shape[1] + 31) // 32)
+        per_sweep = ncell * pv
+        with torch.cuda.stream(s):
+            pts._state.engine.run_windows(-(-(max_iter + 1) // per_sweep), pv, nw, t0=float(t0), alpha_t=float(np.power(alpha_t, per_sweep)),
+                                          t_target=float(t_target), seed=seed, read_counters=False)
+    out = []
+    for pts, s in states:  # phase 3: collect
+        with torch.cuda.stream(s):
+            pts._state.refresh_from_device()
+            out.append(list(pts._state.objects()))
+    for s in streams:
+        main.wait_stream(s)
+    return out
+
+
+def kernel_probabilities_default():
+    from ..engine import kernel_probabilities
+    return kernel_probabilities()

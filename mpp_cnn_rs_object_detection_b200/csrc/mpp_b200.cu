@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1349,7 +1350,12 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_windows_dataflow<R, NW, DBG>, 32 * NW, smem));
         if (blocks_per_sm < 1) return fail(MPP_ERR_CUDA, "k_windows_dataflow does not fit on an SM");
     }
-    const int grid = std::min(total, blocks_per_sm * h->num_sms);  // all CTAs co-resident: the in-order task queue needs it
+    // persistent grid: never more CTAs than fit on the device (only CTAs that are running claim tasks, so the in-order
+    // queue cannot deadlock), and not many more than can ever be active at once (about two colour classes of windows),
+    // so that small scenes leave room for other contexts' kernels running concurrently on other streams
+    const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
+    static const int cap_factor_x2 = getenv("MPP_GRID_CAP_X2") ? atoi(getenv("MPP_GRID_CAP_X2")) : 1;  // grid <= cap/2 colour classes
+    const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_factor_x2 * per_colour / 2 + 8));
     k_windows_dataflow<R, NW, DBG><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
     return MPP_OK;
