@@ -760,8 +760,11 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef MPP_DF_MIN_BLOCKS
+#define MPP_DF_MIN_BLOCKS 1
+#endif
 template <typename R, int NW, bool DBG>
-__global__ void __launch_bounds__(32 * NW) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
+__global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
                                                              uint32_t uid_base, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
     WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);

@@ -89,10 +89,9 @@ def mark_classes(objs: np.ndarray) -> np.ndarray:
     return out
 
 
-def make_scene(seed: int, shape: Tuple[int, int], n_rect: int, blob_sigma: float = 2.0, peak: float = 0.8,
-               peak_radius: int = 4):
-    """numpy scene: returns (objects (N,5) f64, det (H,W) f32, marks [3 x (H,W,32) f32])."""
-    objs = make_objects(seed, shape, n_rect)
+def make_maps(objs: np.ndarray, shape: Tuple[int, int], seed: int, blob_sigma: float = 2.0, peak: float = 0.8, peak_radius: int = 4):
+    """Detection map and mark maps consistent with the given objects ((N,5) rows x, y, size, ratio, angle); the random
+    background is drawn from default_rng(seed + 1).  Returns (det (H,W) f32, marks [3 x (H,W,32) f32])."""
     h, w = shape
     rng = np.random.default_rng(seed + 1)
     det = np.full((h, w), 0.02, dtype=np.float32)
@@ -119,6 +118,14 @@ def make_scene(seed: int, shape: Tuple[int, int], n_rect: int, blob_sigma: float
             win[..., c[i]] = peak
             win /= win.sum(-1, keepdims=True)
         marks.append(np.ascontiguousarray(m, dtype=np.float32))
+    return det, marks
+
+
+def make_scene(seed: int, shape: Tuple[int, int], n_rect: int, blob_sigma: float = 2.0, peak: float = 0.8,
+               peak_radius: int = 4):
+    """numpy scene: returns (objects (N,5) f64, det (H,W) f32, marks [3 x (H,W,32) f32])."""
+    objs = make_objects(seed, shape, n_rect)
+    det, marks = make_maps(objs, shape, seed, blob_sigma, peak, peak_radius)
     return objs, det, marks
 
 
