@@ -761,7 +761,7 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 }
 
 #ifndef MPP_DF_MIN_BLOCKS
-#define MPP_DF_MIN_BLOCKS 1
+#define MPP_DF_MIN_BLOCKS 2
 #endif
 template <typename R, int NW, bool DBG>
 __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
