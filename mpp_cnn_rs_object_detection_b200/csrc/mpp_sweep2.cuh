@@ -522,24 +522,33 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
     const int n = w.n;
     R n_o1 = 0, n_o2 = 0, n_a1 = 0, n_a2 = 0;
     int n_ao = -1, n_aa = -1, n_ao2 = -1, n_aa2 = -1;
+    bool any_pair = false;
     for (int k = lane; k < n; k += 32) {
         if (k == s || !(w.flags[k] & W2_ALIVE)) continue;
         // the removed object was this entry's best or second-best partner: its top-2 must be rescanned
         const bool redo_ov = r >= 0 && (w.aov[k] == r || w.aov2[k] == r), redo_al = r >= 0 && (w.aal[k] == r || w.aal2[k] == r);
         if (s >= 0) {
             const R o = po[k], al = pa[k];
-            if (o > n_o1) { n_o2 = n_o1; n_ao2 = n_ao; n_o1 = o; n_ao = k; } else if (o > n_o2) { n_o2 = o; n_ao2 = k; }
-            if (al > n_a1) { n_a2 = n_a1; n_aa2 = n_aa; n_a1 = al; n_aa = k; } else if (al > n_a2) { n_a2 = al; n_aa2 = k; }
-            if (!redo_ov && (w.flags[k] & W2_INNER)) {
-                if (o > w.ov1[k]) { w.ov2[k] = w.ov1[k]; w.aov2[k] = w.aov[k]; w.ov1[k] = o; w.aov[k] = (short)s; }
-                else if (o > w.ov2[k]) { w.ov2[k] = o; w.aov2[k] = (short)s; }
-            }
-            if (!redo_al && (w.flags[k] & W2_INNER)) {
-                if (al > w.al1[k]) { w.al2[k] = w.al1[k]; w.aal2[k] = w.aal[k]; w.al1[k] = al; w.aal[k] = (short)s; }
-                else if (al > w.al2[k]) { w.al2[k] = al; w.aal2[k] = (short)s; }
+            if (o > (R)0 || al > (R)0) {  // isolated objects (the common case) skip all of this
+                any_pair = true;
+                if (o > n_o1) { n_o2 = n_o1; n_ao2 = n_ao; n_o1 = o; n_ao = k; } else if (o > n_o2) { n_o2 = o; n_ao2 = k; }
+                if (al > n_a1) { n_a2 = n_a1; n_aa2 = n_aa; n_a1 = al; n_aa = k; } else if (al > n_a2) { n_a2 = al; n_aa2 = k; }
+                if (!redo_ov && (w.flags[k] & W2_INNER)) {
+                    if (o > w.ov1[k]) { w.ov2[k] = w.ov1[k]; w.aov2[k] = w.aov[k]; w.ov1[k] = o; w.aov[k] = (short)s; }
+                    else if (o > w.ov2[k]) { w.ov2[k] = o; w.aov2[k] = (short)s; }
+                }
+                if (!redo_al && (w.flags[k] & W2_INNER)) {
+                    if (al > w.al1[k]) { w.al2[k] = w.al1[k]; w.aal2[k] = w.aal[k]; w.al1[k] = al; w.aal[k] = (short)s; }
+                    else if (al > w.al2[k]) { w.al2[k] = al; w.aal2[k] = (short)s; }
+                }
             }
         }
         if ((redo_ov || redo_al) && (w.flags[k] & W2_INNER)) recompute_top2(m, w, k, redo_ov, redo_al, sx, sy);
+    }
+    if (s >= 0 && !__any_sync(MPP_FULL, any_pair)) {  // no partner within reach of the new object
+        if (lane == 0) { w.ov1[s] = 0; w.ov2[s] = 0; w.al1[s] = 0; w.al2[s] = 0; w.aov[s] = -1; w.aov2[s] = -1; w.aal[s] = -1; w.aal2[s] = -1; }
+        __syncwarp();
+        return;
     }
     if (s >= 0) {  // merge the per-lane top-2 of (po, pa) into the new object's reductions (ties: lowest lane first)
         const R mo = warp_max(n_o1);
@@ -577,6 +586,15 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     const ModelDev &m = c.m;
     const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
     const int x0 = max(px0, 0), x1 = min(px0 + 32, c.H), y0 = max(py0, 0), y1 = min(py0 + 32, c.W);
+#ifdef MPP_TRACE
+    long long t_mark[8];
+    t_mark[0] = clock64();
+    long long t_eval = 0, t_commit = 0;
+    int n_rounds = 0;
+#define MPP_MARK(i) t_mark[i] = clock64()
+#else
+#define MPP_MARK(i)
+#endif
 
     // ------------------------------------------------------------------ staging
     // phase A (warp 0): window constants; handles / position keys of the objects within 64 px of the window
@@ -640,6 +658,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         if (lane == 0) { w.n = n; w.n_win = 0; }
     }
     __syncthreads();
+    MPP_MARK(1);
     const int n0 = w.n;
     // phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
     for (int k = threadIdx.x; k < n0; k += 32 * NW) {
@@ -653,6 +672,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         w.order[rank] = w.handle[k];
     }
     __syncthreads();
+    MPP_MARK(2);
     // phase C: one thread per object loads its full record
     for (int p = threadIdx.x; p < n0; p += 32 * NW) {
         const uint32_t h = w.order[p];
@@ -667,6 +687,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         if (inw) atomicAdd(&w.n_win, 1);
     }
     __syncthreads();
+    MPP_MARK(3);
     // phase D: per-mark details of the window objects (deaths, translations, mark transforms), one warp per object;
     // phase E: partner reductions of everything a move in the window can affect, one thread per object
     for (int k = warp; k < n0; k += NW) {
@@ -681,16 +702,23 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     for (int k = threadIdx.x; k < n0; k += 32 * NW)
         if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, true, true, sx, sy);
     __syncthreads();
+    MPP_MARK(4);
 
     // ------------------------------------------------------------------ speculative proposal rounds
     int it = 0;
     while (it < per_visit) {
         Eval<R> e;
         const int mine = it + warp;
+#ifdef MPP_TRACE
+        const long long t_a = clock64();
+#endif
         if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff);
         else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; }
         if (lane == 0) { w.res_accept[warp] = e.accept ? 1 : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
         __syncthreads();
+#ifdef MPP_TRACE
+        const long long t_b = clock64();
+#endif
         int first = NW;
 #pragma unroll
         for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q]) first = q;
@@ -706,8 +734,22 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             else commit_proposal(c, w, e, mine, lane, sx, sy, po, pa);
         }
         __syncthreads();
+#ifdef MPP_TRACE
+        t_eval += t_b - t_a; t_commit += clock64() - t_b; ++n_rounds;
+#endif
         it += used;
     }
+#ifdef MPP_TRACE
+    if (dbg_maxdiff && threadIdx.x == 0) {
+        const int slot = atomicAdd(reinterpret_cast<int *>(dbg_maxdiff + 1), 1);
+        if (slot < 4000) {
+            float *o = dbg_maxdiff + 8 + slot * 12;
+            o[0] = (float)w.n; o[1] = (float)w.n_win; o[2] = (float)(t_mark[1] - t_mark[0]); o[3] = (float)(t_mark[2] - t_mark[1]);
+            o[4] = (float)(t_mark[3] - t_mark[2]); o[5] = (float)(t_mark[4] - t_mark[3]); o[6] = (float)t_eval; o[7] = (float)t_commit;
+            o[8] = (float)n_rounds; o[9] = (float)w.n_acc; o[10] = (float)(clock64() - t_mark[0]); o[11] = (float)w.n_eval;
+        }
+    }
+#endif
     if (threadIdx.x == 0) {
         if (w.masks_dirty) {
             __threadfence();  // records before masks: a window staging these cells must never see a mask bit without its record

@@ -1,0 +1,30 @@
+"""Per-visit phase timing of the window sampler (needs a library built with -DMPP_TRACE; development tool)."""
+import sys, os, ctypes as C
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from mpp_cnn_rs_object_detection_b200 import synth, _lib
+from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec
+size = 2048
+dev = torch.device("cuda", 0)
+objs, det, marks = synth.make_scene_torch(0, (size, size), 2600, dev)
+Cc, H = bench.CALIB_HRCM, bench.HRC
+spec = ModelSpec(setup="legacy", pos_threshold=Cc["detection_threshold"], remap_coefs=Cc["coefs"], remap_intercepts=Cc["intercepts"],
+                 min_area=Cc["min_area"], max_area=Cc["max_area"], combinator="hierarchical",
+                 comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
+for nw, pv in ((8, 32), (4, 32)):
+    eng = Engine((size, size), device=dev)
+    eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
+    eng.add_objects(objs[:, :2], objs[:, 2:5])
+    eng.run_windows(3, pv, nw, t0=0.02, seed=1)
+    dbg = torch.zeros(8 + 4000 * 12, dtype=torch.float32, device=dev)
+    cnt = (C.c_ulonglong * 8)()
+    _lib.check(eng.lib.mpp_run_windows(eng.ctx, 1, pv, nw, 1, 0.02, 1.0, 0.0, 1, 3, cnt, dbg.data_ptr()))
+    d = dbg.cpu().numpy()
+    n = min(4000, int(d[1:2].view(np.int32)[0]))
+    tr = d[8:8 + n * 12].reshape(n, 12)
+    print(f"nw={nw} pv={pv}: visits traced {n}")
+    for name, col in (("staged n", 0), ("n_win", 1), ("A heads us", 2), ("B rank us", 3), ("C recs us", 4), ("D+E us", 5), ("eval us", 6), ("commit us", 7),
+                      ("rounds", 8), ("acc", 9), ("total us", 10), ("evaluated", 11)):
+        v = tr[:, col] / 1900.0 if "us" in name else tr[:, col]
+        print(f"  {name:12s} mean {v.mean():8.2f}  p50 {np.median(v):8.2f}  p90 {np.percentile(v, 90):8.2f}  max {v.max():8.2f}")
