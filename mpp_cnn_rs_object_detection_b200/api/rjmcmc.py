@@ -225,7 +225,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         st.add_many(image_data.gt_config)
     elif isinstance(init_config, str) and init_config == "naive":
         st.engine.naive_init(float(energy_setup.detection_threshold), 6.0)
-        st.refresh_from_device()
+        if sampler != "parallel":
+            st.refresh_from_device()  # the parallel sampler only needs the count; the host mirror is rebuilt once at the end
     elif init_config is not None:
         st.add_many(list(init_config))
     points.energy_graph._members = dict.fromkeys(st.handle_of)
@@ -238,7 +239,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         alpha_t = np.power(target_temperature / init_temperature, 1 / burn_in)
         target_temperature = 0
     burn_in, samples_interval = int(burn_in), int(samples_interval)
-    intensity = max(1, len(st))  # :68
+    intensity = max(1, len(st.engine))  # :68
     kernels, p_kernels = make_kernels(image_data, intensity=intensity, rng=rng, use_split_merge=use_split_merge)
     max_iter = burn_in + (num_samples + 1) * samples_interval  # :78
     start = time.perf_counter()
@@ -257,7 +258,9 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         stats = {"proposals": 0, "accepted": 0, "births": 0, "deaths": 0, "evaluated": 0, "sweeps": 0}
         seed = int(rng.integers(0, 2 ** 62))
         # snapshot steps of the reference's sampling_rule, expressed in sweeps
-        snap_steps = [s for s in range(burn_in, max_iter + 1) if s % samples_interval == 0] if samples_interval > 0 else []
+        # num_samples == 1: the reference returns its last snapshot, at most samples_interval - 1 steps before the end of the
+        # chain; the final state is returned here instead (no intermediate read-back)
+        snap_steps = [s for s in range(burn_in, max_iter + 1) if s % samples_interval == 0] if (samples_interval > 0 and num_samples > 1) else []
         snap_sweeps = sorted({-(-(s + 1) // per_sweep) for s in snap_steps})
         total_sweeps = -(-(max_iter + 1) // per_sweep)
         alpha_sweep = float(np.power(alpha_t, per_sweep))
