@@ -10,7 +10,8 @@ from .energy_graph import EnergyGraph  # noqa: F401
 from .energy_point_set import EPointsSet  # noqa: F401
 from .energy_setups import EnergySetup, LegacyEnergiesCalibration, LegacyEnergySetup, NoCalibEnergiesCalibration, NoCalibrationEnergySetup  # noqa: F401
 from .kernels import (BirthKernel, DataDrivenShapeTransformKernel, DataDrivenTranslationKernel, DeathKernel,  # noqa: F401
-                      GaussianShapeTransformKernel, GaussianTranslationKernel, Kernel, make_kernels)
+                      GaussianShapeTransformKernel, GaussianTranslationKernel, Kernel, MergeKernel, SplitKernel, SplitSampler,
+                      make_kernels)
 from .mappings import ValueMapping, default_mappings, output_vector_to_value  # noqa: F401
 from .point_set import PointsSet  # noqa: F401
 from .rjmcmc import RJMCMC, StopOnMaxIter, naive_detection, nms_distance, sample_rjmcmc, sample_rjmcmc_batch, sample_rjmcmc_tiles  # noqa: F401

@@ -181,17 +181,35 @@ class EnergyGraph:
         for r in removed:
             if r not in st.handle_of:
                 raise KeyError(r)
-        if len(removed) > 1 or len(added) > 1:
-            raise NotImplementedError("perturbations with several removals / additions (split & merge kernels, "
-                                      "split_and_merge_kernels.py) are not built yet")
         if not removed and not added:
             return 0.0
         fused = energy_combinator is None or hasattr(energy_combinator, "device_params")
-        if fused:
-            st.use_combinator(energy_combinator)
+        if not fused:
+            return self._delta_plugin(st, removed, added, energy_combinator)
+        st.use_combinator(energy_combinator)
+        if len(removed) <= 1 and len(added) <= 1:
             rec = st.proposal_record(removed[0] if removed else None, added[0] if added else None)
             return float(st.engine.delta_batch(rec)[0])
-        return self._delta_plugin(st, removed, added, energy_combinator)
+        return self._delta_multi(st, removed, added)
+
+    def _delta_multi(self, st: DeviceState, removed, added) -> float:
+        """Perturbations with several removals / additions (split & merge kernels): the energy is a function of the state, so
+        the difference telescopes into single-object Delta-energies evaluated on the device while the state is stepped through
+        the intermediate configurations; the state is restored afterwards (mutate-and-revert, like energy_graph.py:191-223)."""
+        total, undo = 0.0, []
+        try:
+            for q in removed:
+                total += float(st.engine.delta_batch(st.proposal_record(q, None))[0])
+                st.remove(q)
+                undo.append(("add", q))
+            for a in added:
+                total += float(st.engine.delta_batch(st.proposal_record(None, a))[0])
+                st.add(a)
+                undo.append(("remove", a))
+        finally:
+            for op, u in reversed(undo):
+                (st.add if op == "add" else st.remove)(u)
+        return total
 
     def _delta_plugin(self, st: DeviceState, removed, added, combinator) -> float:
         """Plug-in (Python) combinator: the reference's own recipe on device-computed vectors -- 3x3-cell neighbourhoods of

@@ -146,18 +146,122 @@ class DataDrivenShapeTransformKernel(DeviceKernel):  # transform_kernels.py:162-
     KERNEL_ID = 7
 
 
+# ---------------------------------------------------------------------------------------------- optional split / merge
+class SplitSampler:  # split_and_merge_kernels.py:14-36
+    def __init__(self, pos_radius: float, shape_sigmas: List[float], mappings):
+        self.pos_radius, self.shape_sigmas, self.mappings = pos_radius, shape_sigmas, mappings
+        self.scaled_shaped_sigmas = [s * m.range for m, s in zip(mappings, shape_sigmas)]
+        self.n_params = len(Rectangle.PARAMETERS)
+
+    def sample(self, rng: np.random.Generator):
+        pos = rng.uniform((0, 0), self.pos_radius)
+        while np.linalg.norm(pos) > self.pos_radius:
+            pos = rng.uniform((0, 0), self.pos_radius)
+        return pos, rng.normal((0,) * self.n_params, self.scaled_shaped_sigmas)
+
+    def pdf(self, pos_deltas, shape_deltas) -> float:
+        p_pos = 1 / (np.pi * self.pos_radius * self.pos_radius)
+        p_shape = [np.exp(-(d / s) ** 2 / 2) / (np.sqrt(2 * np.pi) * s) for d, s in zip(shape_deltas, self.scaled_shaped_sigmas)]
+        return float(p_pos * np.prod(p_shape))
+
+
+class _SplitMergeBase(Kernel):
+    """The optional two-object moves (use_split_merge=False in both shipped configurations).  Draws follow the reference's
+    numpy calls; neighbourhood counts come from the device index and the Delta-energy of the two-object perturbation from
+    the device (EnergyGraph._delta_multi).  They run through the step-by-step RJMCMC loop only."""
+
+    def __init__(self, p_split: float, p_merge: float, split_sampler: SplitSampler, support_shape, intensity: float, merge_radius: float):
+        self.p_split, self.p_merge, self.split_sampler = p_split, p_merge, split_sampler
+        self.shape, self.intensity, self.radius = support_shape, intensity, merge_radius
+        assert self.radius == self.split_sampler.pos_radius
+
+
+class SplitKernel(_SplitMergeBase):  # split_and_merge_kernels.py:39-107
+    def sample_perturbation(self, x: PointsSet, rng: np.random.Generator) -> Perturbation:
+        if len(x) == 0:
+            return Perturbation(self.__class__)
+        p = x.random_choice(rng)
+        pos_delta, shape_delta = self.split_sampler.sample(rng)
+        new = []
+        for sgn in (-1, +1):
+            marks = {a: m.clip(getattr(p, a) + sgn * d) for a, d, m in zip(Rectangle.PARAMETERS, shape_delta, self.split_sampler.mappings)}
+            new.append(Rectangle(x=int(np.clip(p.x + sgn * pos_delta[0], 0, self.shape[0] - 1)),
+                                 y=int(np.clip(p.y + sgn * pos_delta[1], 0, self.shape[1] - 1)), **marks))
+        return Perturbation(self.__class__, addition=new, removal=p, data={"pos_delta": pos_delta, "shape_delta": shape_delta})
+
+    def forward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        assert u.type == self.__class__
+        n = len(x)
+        if n == 0:
+            return self.p_kernel
+        return self.p_kernel * ((1 / n) * self.split_sampler.pdf(u.data["pos_delta"], u.data["shape_delta"])) / self.intensity
+
+    def backward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        assert u.type == self.__class__
+        n = len(x) + 1
+        if n <= 1:
+            return self.p_merge
+        nb0 = len(x.get_potential_neighbors(u.addition[0], radius=self.radius)) + 1
+        nb1 = len(x.get_potential_neighbors(u.addition[1], radius=self.radius)) + 1
+        return self.p_merge * ((1 / n) * (1 / nb0) + (1 / n) * (1 / nb1))
+
+    @property
+    def p_kernel(self) -> float:
+        return self.p_split
+
+
+class MergeKernel(_SplitMergeBase):  # split_and_merge_kernels.py:110-178
+    def sample_perturbation(self, x: PointsSet, rng: np.random.Generator) -> Perturbation:
+        if len(x) <= 1:
+            return Perturbation(self.__class__)
+        p0 = x.random_choice(rng)
+        neighbors = sorted(x.get_neighbors(p0, radius=self.radius), key=lambda q: (q.x, q.y, x._state.uid_of.get(q, 0)))
+        data = {"n_neighbors": len(neighbors)}
+        if not neighbors:
+            return Perturbation(self.__class__, data=data)
+        p1 = neighbors[int(rng.integers(0, len(neighbors)))]
+        marks = {a: m.clip((getattr(p0, a) + getattr(p1, a)) / 2) for a, m in zip(Rectangle.PARAMETERS, self.split_sampler.mappings)}
+        p_new = Rectangle(x=int(np.clip((p0.x + p1.x) / 2, 0, self.shape[0] - 1)), y=int(np.clip((p0.y + p1.y) / 2, 0, self.shape[0] - 1)),
+                          **marks)  # the reference clips y with shape[0] too (split_and_merge_kernels.py:143)
+        return Perturbation(self.__class__, addition=p_new, removal=[p0, p1], data=data)
+
+    def forward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        assert u.type == self.__class__
+        n = len(x)
+        if n <= 1 or u.data["n_neighbors"] == 0:
+            return self.p_kernel
+        return self.p_kernel * ((1 / n) * (1 / u.data["n_neighbors"]))
+
+    def backward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        assert u.type == self.__class__
+        n = len(x) - 1
+        if n == 0 or u.removal is None:
+            return self.p_split
+        p0, p1 = u.removal[0], u.removal[1]
+        pos_delta = [(p0.x - p1.x) / 2, (p0.y - p1.y) / 2]
+        shape_delta = [(getattr(p0, a) - getattr(p1, a)) / 2 for a in Rectangle.PARAMETERS]
+        return self.p_split * ((1 / n) * self.split_sampler.pdf(pos_delta, shape_delta)) / self.intensity
+
+    @property
+    def p_kernel(self) -> float:
+        return self.p_merge
+
+
 def make_kernels(image_data: ImageWMaps, intensity: float, rng: np.random.Generator = None, use_split_merge: bool = False,
                  kernel_weights=None):
     """The eight kernels in the reference's order with their choice probabilities (make_kernels.py:50-177):
     [UniformBirth, UniformDeath, DataBirth, DataDeath, GaussianTranslation, DataTranslation, GaussianTransform,
-    DataTransform], p = [1/18, 1/18, 1/9, 1/9, 1/9, 2/9, 1/9, 2/9] for the default weights."""
-    if use_split_merge:
-        raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
-    p = kernel_probabilities(weights=kernel_weights)
-    kset = KernelSet(intensity=intensity, p_kernels=p)
+    DataTransform], p = [1/18, 1/18, 1/9, 1/9, 1/9, 2/9, 1/9, 2/9] for the default weights; with use_split_merge two more
+    (SplitKernel, MergeKernel, radius 16, shape sigmas 0.1: make_kernels.py:145-161)."""
+    p = kernel_probabilities(use_split_merge=use_split_merge, weights=kernel_weights)
+    kset = KernelSet(intensity=intensity, p_kernels=p[:8])
     kernels: List[Kernel] = [
         BirthKernel(kset, p[0], data_driven=False), DeathKernel(kset, p[1], data_driven=False),
         BirthKernel(kset, p[2], data_driven=True), DeathKernel(kset, p[3], data_driven=True),
         GaussianTranslationKernel(kset, p[4]), DataDrivenTranslationKernel(kset, p[5]),
         GaussianShapeTransformKernel(kset, p[6]), DataDrivenShapeTransformKernel(kset, p[7])]
+    if use_split_merge:
+        sampler = SplitSampler(pos_radius=16, shape_sigmas=[0.1, 0.1, 0.1], mappings=image_data.mappings)
+        args = dict(p_split=p[8], p_merge=p[9], split_sampler=sampler, support_shape=tuple(image_data.shape[:2]), intensity=intensity, merge_radius=16)
+        kernels += [SplitKernel(**args), MergeKernel(**args)]
     return kernels, p

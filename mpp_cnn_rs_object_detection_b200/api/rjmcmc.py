@@ -214,8 +214,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
     sampler='sequential' the reference's one-proposal-at-a-time chain, run on the device.
     reuse_device_maps    False: always upload the maps (no cache keyed on the host arrays).
     return_stats         True: returns (result, dict of device counters) instead of result."""
-    if use_split_merge:
-        raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
+    if use_split_merge and sampler != "sequential":
+        raise NotImplementedError("the optional split / merge kernels run through the step-by-step chain: pass sampler='sequential'")
     unit_energies, pair_energies = energy_setup.make_energies(image_data)
     points = EPointsSet(points=[], support_shape=image_data.shape, unit_energies_constructors=unit_energies,
                         pair_energies_constructors=pair_energies, precision=precision, reuse_device_maps=reuse_device_maps,

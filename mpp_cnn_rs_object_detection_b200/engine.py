@@ -23,21 +23,27 @@ BASE_KERNEL_WEIGHTS = {"bd_weight": 1, "uniform_bd_weight": 1, "data_bd_weight":
 
 
 def kernel_probabilities(use_split_merge: bool = False, weights=None) -> np.ndarray:
-    """Kernel choice probabilities of make_kernels (rjmcmc_sampler/kernels/make_kernels.py:13-24,76-86,163-166)."""
-    if use_split_merge:
-        raise NotImplementedError("split / merge kernels (split_and_merge_kernels.py) are not built yet")
+    """Kernel choice probabilities of make_kernels (rjmcmc_sampler/kernels/make_kernels.py:13-24,76-86,145-166): 8 entries, or
+    10 with the optional split / merge kernels."""
     w = BASE_KERNEL_WEIGHTS if weights is None else weights
 
     def normalize(a):
         a = np.array(a, dtype=np.float64)
         return a / np.linalg.norm(a, ord=1)
 
-    p_bd, p_trl, p_trf = normalize([w["bd_weight"], w["translation_weight"], w["transformation_weight"]])
+    if use_split_merge:
+        p_bd, p_ms, p_trl, p_trf = normalize([w["bd_weight"], w["ms_weight"], w["translation_weight"], w["transformation_weight"]])
+    else:
+        p_bd, p_trl, p_trf = normalize([w["bd_weight"], w["translation_weight"], w["transformation_weight"]])
+        p_ms = None
     p_bd_unif, p_bd_data = normalize([w["uniform_bd_weight"], w["data_bd_weight"]])
     p_trl_gaus, p_trl_data = normalize([w["gaussian_translation_weight"], w["data_translation_weight"]])
     p_trf_gaus, p_trf_data = normalize([w["gaussian_transformation_weight"], w["data_transformation_weight"]])
-    p = np.array([0.5 * p_bd_unif * p_bd, 0.5 * p_bd_unif * p_bd, 0.5 * p_bd_data * p_bd, 0.5 * p_bd_data * p_bd,
-                  p_trl * p_trl_gaus, p_trl * p_trl_data, p_trf * p_trf_gaus, p_trf * p_trf_data])
+    p = [0.5 * p_bd_unif * p_bd, 0.5 * p_bd_unif * p_bd, 0.5 * p_bd_data * p_bd, 0.5 * p_bd_data * p_bd,
+         p_trl * p_trl_gaus, p_trl * p_trl_data, p_trf * p_trf_gaus, p_trf * p_trf_data]
+    if use_split_merge:
+        p += [p_ms * 0.5, p_ms * 0.5]
+    p = np.array(p)
     if abs(1 - np.sum(p)) < 1e-8:
         p = p / np.sum(p)
     return p

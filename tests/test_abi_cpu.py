@@ -109,8 +109,11 @@ def test_term_translation_and_rejections():
         build_layout([], [api.DistanceIndicatorPairEnergy("p", 64.0)])
     with pytest.raises(AssertionError):
         build_layout([api.ConstantUnitEnergy("a", 1.0), api.ConstantUnitEnergy("a", 2.0)], [])
+    kernels, p10 = api.make_kernels(img, 1.0, use_split_merge=True)  # optional split / merge kernels (make_kernels.py:145-166)
+    assert len(kernels) == 10 and isinstance(kernels[8], api.SplitKernel) and isinstance(kernels[9], api.MergeKernel)
+    np.testing.assert_allclose(p10 * 24, [1, 1, 2, 2, 2, 4, 2, 4, 3, 3], rtol=1e-15)
     with pytest.raises(NotImplementedError):
-        api.make_kernels(img, 1.0, use_split_merge=True)
+        api.sample_rjmcmc(img, np.random.default_rng(0), 1, None, None, 1.0, 0.99, 10, legacy, 1, 0.0, use_split_merge=True)
 
 
 def test_shapes_and_mappings_match_golden():

@@ -351,3 +351,44 @@ def test_mpp_model_infer_and_cli(tmp_path):
     assert len(out) == 1 and "detection_score" in out[0]
     with pytest.raises(ValueError):
         cli(["-p", "train", "-m", "mpp", "-c", os.path.join(gold, "model_mpp_hrcM", "config.json")])
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_split_merge_kernels_match_reference(cfg):
+    """Optional two-object moves: Delta-energy of list perturbations and forward / backward probabilities
+    against the reference's own values; a short chain with all ten kernels runs through RJMCMC.step."""
+    api = _api()
+    g = gu.load(f"split_merge_{cfg}.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, cfg)
+    img = _image(api, det, marks)
+    unit, pair = setup.make_energies(img)
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    eps = api.EPointsSet(rects, det.shape, unit, pair)
+    kernels, p = api.make_kernels(img, intensity=float(g["intensity"]), rng=np.random.default_rng(0), use_split_merge=True)
+    np.testing.assert_allclose(p, g["p_kernels"], rtol=1e-15)
+    for row in g["rows"]:
+        kid, r0, r1 = int(row[0]), int(row[1]), int(row[2])
+        rem = [rects[k] for k in (r0, r1) if k >= 0]
+        add = [api.Rectangle(int(row[3 + 5 * j]), int(row[4 + 5 * j]), row[5 + 5 * j], row[6 + 5 * j], row[7 + 5 * j]) for j in range(2)
+               if not np.isnan(row[3 + 5 * j])]
+        if kid == 8:
+            u = api.Perturbation(api.SplitKernel, removal=rem[0] if rem else None, addition=add or None,
+                                 data={"pos_delta": row[13:15], "shape_delta": row[15:18]})
+        else:
+            u = api.Perturbation(api.MergeKernel, removal=rem or None, addition=add[0] if add else None, data={"n_neighbors": int(row[18])})
+        f, b = kernels[kid].forward_probability(eps.points, u), kernels[kid].backward_probability(eps.points, u)
+        assert abs(f - row[21]) <= 1e-9 * abs(row[21]) and abs(b - row[22]) <= 1e-9 * abs(row[22]), (kid, f, row[21], b, row[22])
+        if rem or add:
+            assert abs(eps.energy_delta(u, energy_combinator=comb) - row[20]) < 4e-5 + 1e-5 * abs(row[20])
+            assert abs(eps.energy_delta(u) - row[19]) < 8e-5 + 1e-5 * abs(row[19])
+            assert len(eps) == len(rects)  # mutate-and-revert left the state untouched
+    vec = eps.energy_graph.compute_subset(rects, return_vector=True)
+    names = [str(s) for s in gu.load(f"energies_{cfg}.npz")["names"]]
+    np.testing.assert_allclose(np.array([vec[k] for k in names]).T, gu.load(f"energies_{cfg}.npz")["vectors"], rtol=1e-5, atol=1e-5)
+    chain = api.RJMCMC(t0=0.05, kernels=kernels, p_kernels=p, initial_state=eps, stopping_condition=api.StopOnMaxIter(150),
+                       rng=np.random.default_rng(1), energy_combinator=comb, alpha_t=1.0)
+    states, summaries = chain.run()
+    kinds = {s.kernel for s in summaries[1:]}
+    assert api.SplitKernel in kinds and api.MergeKernel in kinds and len(summaries) == 152
+    assert summaries[-1].n_points == len(states[-1])

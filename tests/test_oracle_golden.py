@@ -145,3 +145,28 @@ def test_reference_known_answers():
     assert ka["epointsset_total_energy"] == [5.0, 8.0, 6.0]
     assert ka["epointsset_energy_delta"] == [-1.0, 1.0]
     assert ka["pointsset_grid_200x516_r32"] == [7, 17]
+
+
+@pytest.mark.parametrize("cfg", ["legacy", "nocalib"])
+def test_split_merge_kernels_match_reference(cfg):
+    """Optional 2-object moves (R24): Delta-energies of list perturbations and the kernels' forward / backward probabilities."""
+    g = gu.load(f"split_merge_{cfg}.npz")
+    _, det, marks = gu.scene_inputs(g)
+    scene, comb = make_oracle_scene(cfg, det, marks)
+    config = [orc.ORect(*r) for r in g["config"]]
+    state = orc.OracleState(scene, config)
+    p = orc.kernel_probabilities_split_merge()
+    np.testing.assert_allclose(p, g["p_kernels"], rtol=1e-15)
+    lam = float(g["intensity"])
+    for row in g["rows"]:
+        kid, r0, r1 = int(row[0]), int(row[1]), int(row[2])
+        rem = [config[k] for k in (r0, r1) if k >= 0]
+        add = [orc.ORect(*row[3 + 5 * j:8 + 5 * j]) for j in range(2) if not np.isnan(row[3 + 5 * j])]
+        if kid == 8:
+            f, b = orc.split_forward_backward(state, p[8], p[9], lam, add, row[13:15], row[15:18])
+        else:
+            f, b = orc.merge_forward_backward(state, p[8], p[9], lam, rem, int(row[18]))
+        assert abs(f - row[21]) <= 1e-12 * abs(row[21]) and abs(b - row[22]) <= 1e-12 * abs(row[22]), (kid, f, row[21], b, row[22])
+        if rem or add:
+            assert abs(state.delta(rem, add) - row[19]) < 4e-5
+            assert abs(state.delta(rem, add, comb) - row[20]) < 1e-9
