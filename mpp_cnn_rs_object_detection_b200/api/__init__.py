@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's Python interface for the MPP sampling path: same class
 and function names, argument meaning and error behaviour as models/mpp, base/shapes and models/shape_net/mappings in the
 reference; all computation goes through the C ABI of include/mpp_b200.h to the CUDA kernels."""
-from .combination import HierarchicalEnergyCombinator, LogisticEnergyCombinator, ManualHierarchicalEnergyCombinator  # noqa: F401
+from .combination import (HierarchicalEnergyCombinator, LogisticEnergyCombinator, ManualHierarchicalEnergyCombinator,  # noqa: F401
+                          MLPEnergyCombinator)
 from .custom_types import EnergyCombinationModel, ImageWMaps, Perturbation, RJMCMCStateSummary  # noqa: F401
 from .energies import (AreaPriorEnergy, ConstantUnitEnergy, DistanceIndicatorPairEnergy, PairEnergy, PairEnergyConstructor,  # noqa: F401
                        PositionEnergy, RatioPriorEnergy, RectangleOverlapEnergy, ShapeAlignmentEnergy, ShapeEnergy,

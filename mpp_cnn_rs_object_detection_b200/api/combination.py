@@ -86,3 +86,24 @@ class LogisticEnergyCombinator(EnergyCombinationModel):  # logistic.py:14-26
         setup = "legacy" if names == LEGACY_NAMES else "nocalib"
         spec = ModelSpec(setup=setup, ratio_prior=len(names) == 8, combinator=kind, comb_w=w, comb_bias=b, comb_threshold=t)
         return combine_on_device(spec, m)[1]
+
+
+@dataclass
+class MLPEnergyCombinator(EnergyCombinationModel):  # combination/mlp.py:13-27
+    """A torch module over the per-object energy vectors: sum(2*model(v) - 1) (or sum(model(v)) when raw_energy).  It is a
+    plug-in combinator: the vectors are computed by the CUDA kernels, the module is evaluated by PyTorch on the same device,
+    and Delta-energies go through the reference's before / after recipe (EnergyGraph._delta_plugin) instead of the fused
+    kernels -- usable with the step-by-step chain, not with the parallel sampler."""
+    model: "object"
+    energy_names: List[str]
+    raw_energy: bool = False
+
+    def compute(self, vectors: ConfigurationEnergyVector) -> float:
+        import torch
+        if len(vectors[self.energy_names[0]]) == 0:
+            return 0.0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = torch.as_tensor(np.stack([np.asarray(vectors[k], dtype=np.float32) for k in self.energy_names], axis=-1), device=dev)
+        with torch.no_grad():
+            y = self.model.to(dev).forward(x)
+            return float((2 * y - 1).sum().item()) if not self.raw_energy else float(y.sum().item())

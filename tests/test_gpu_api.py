@@ -392,3 +392,32 @@ def test_split_merge_kernels_match_reference(cfg):
     kinds = {s.kernel for s in summaries[1:]}
     assert api.SplitKernel in kinds and api.MergeKernel in kinds and len(summaries) == 152
     assert summaries[-1].n_points == len(states[-1])
+
+
+def test_plugin_combinators_mlp_and_manual():
+    """Combinators that are not fused into the kernels (a torch MLP) go through the before / after recipe on device-computed
+    vectors; the manual hierarchical combinator is fused.  Both must satisfy E(after) - E(before) == energy_delta."""
+    import torch
+    api = _api()
+    g = gu.load("energies_nocalib.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, _ = _setup(api, "nocalib")
+    img = _image(api, det, marks)
+    unit, pair = setup.make_energies(img)
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    torch.manual_seed(0)
+    mlp = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1), torch.nn.Sigmoid())
+    combs = [api.MLPEnergyCombinator(model=mlp, energy_names=setup.energy_names),
+             api.ManualHierarchicalEnergyCombinator(weights_dict={k: 0.3 + 0.1 * i for i, k in enumerate(setup.energy_names)},
+                                                    indicator_energy="PositionEnergy", detection_threshold=0.0)]
+    for comb in combs:
+        eps = api.EPointsSet(rects, det.shape, unit, pair)
+        e0 = eps.energy_graph.compute_subset(list(eps), energy_combinator=comb)
+        for k, (ri, add) in enumerate(list(zip(g["pert_removal"], g["pert_addition"]))[:25]):
+            rem = rects[ri] if ri >= 0 else None
+            a = None if np.isnan(add[0]) else api.Rectangle(int(add[0]), int(add[1]), add[2], add[3], add[4])
+            p = api.Perturbation(type=api.BirthKernel, removal=rem, addition=a)
+            d = eps.energy_delta(p, energy_combinator=comb)
+            after = eps.apply_perturbation(p)
+            e1 = after.energy_graph.compute_subset(list(after), energy_combinator=comb)
+            assert abs((e1 - e0) - d) < 2e-4 + 1e-5 * abs(e0), (type(comb).__name__, k, e1 - e0, d)
