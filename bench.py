@@ -36,6 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes (read + write) per evaluated proposal of k_windows_dataflow<float,8>, from the ncu --set full capture
+# profiles/r01_prof_dataflow_raw.csv: (259.9168 + 34.889984) MB for 531 615 evaluated proposals in the launch
+NCU_DRAM_BYTES_PER_PROPOSAL = 554.5
 METRIC = "rjmcmc_proposals_per_sec"
 UNIT = "proposals/s"
 
@@ -445,8 +448,11 @@ def run_b200(args):
     else:
         sweep_launches = args.steps * args.sweeps * (9 if args.sampler == "windows" else args.stride * args.stride)
     achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
+    per_launch = proposals / world / sweep_launches
+    traffic = NCU_DRAM_BYTES_PER_PROPOSAL * per_launch if (args.sampler == "windows" and args.schedule == "dataflow" and args.warps == 8) else None
     roofline = {"bound": "hbm", "kernel": ("k_windows_dataflow<float,%d>" % args.warps if args.schedule == "dataflow" else "k_sweep2<float,%d>" % args.warps) if args.sampler == "windows" else "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per evaluated proposal x proposals of this launch)",
+                "algorithmic_bytes_per_launch": bpp * per_launch, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
                 "proposals_per_launch": proposals / world / sweep_launches, "us_per_launch": 1e3 * ms / sweep_launches,
                 "note": "latency/parallelism-bound Markov chain: see DESIGN.md"}
 

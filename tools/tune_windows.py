@@ -15,13 +15,15 @@ C, H = bench.CALIB_HRCM, bench.HRC
 spec = ModelSpec(setup="legacy", pos_threshold=C["detection_threshold"], remap_coefs=C["coefs"], remap_intercepts=C["intercepts"],
                  min_area=C["min_area"], max_area=C["max_area"], combinator="hierarchical",
                  comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
-for nw, pv, sched in ((4, 16, "colours"), (4, 32, "colours"), (1, 16, "dataflow"), (2, 16, "dataflow"), (4, 8, "dataflow"), (4, 16, "dataflow"),
-                      (4, 32, "dataflow"), (8, 16, "dataflow"), (8, 32, "dataflow"), (8, 64, "dataflow"), (2, 32, "dataflow")):
+configs = ((1, 32, "dataflow"), (2, 32, "dataflow"), (4, 32, "dataflow"), (8, 32, "dataflow"), (2, 16, "dataflow"), (4, 16, "dataflow")) if size > 2048 else \
+    ((4, 16, "colours"), (4, 32, "colours"), (1, 16, "dataflow"), (2, 16, "dataflow"), (4, 16, "dataflow"), (4, 32, "dataflow"), (8, 16, "dataflow"),
+     (8, 32, "dataflow"), (8, 64, "dataflow"), (2, 32, "dataflow"))
+for nw, pv, sched in configs:
     eng = Engine((size, size), device=dev)
     eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
     eng.add_objects(objs[:, :2], objs[:, 2:5])
     eng.run_windows(5, pv, nw, t0=temp, seed=1, schedule=sched)
-    sweeps = 20
+    sweeps = 20 if size <= 2048 else 4
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -32,13 +34,3 @@ for nw, pv, sched in ((4, 16, "colours"), (4, 32, "colours"), (1, 16, "dataflow"
     print(f"{sched} nw={nw} pv={pv}: {ms / sweeps * 1e3:.0f} us/sweep, attempted {c[0] / ms / 1e3:.1f} M/s, evaluated {c[4] / ms / 1e3:.1f} M/s, "
           f"acc {c[1] / max(1, c[4]):.3f}, n={len(eng)}", flush=True)
     eng.close()
-# v1 for comparison
-eng = Engine((size, size), device=dev)
-eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
-eng.add_objects(objs[:, :2], objs[:, 2:5])
-eng.run_sweeps(5, 8, 3, t0=temp, seed=1)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); eng.run_sweeps(20, 8, 3, t0=temp, seed=1, sweep_offset=5, read_counters=False); e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1); c = eng.run_sweeps(0, 8, 3, t0=temp)
-print(f"v1 cells pv=8: {ms / 20 / 9 * 1e3:.1f} us/launch, attempted {c[0] / ms / 1e3:.1f} M/s, evaluated {c[4] / ms / 1e3:.1f} M/s, n={len(eng)}")
