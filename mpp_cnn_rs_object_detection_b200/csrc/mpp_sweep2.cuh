@@ -72,22 +72,27 @@ __device__ __forceinline__ void shape_terms(const ModelDev &m, R dm0, R dm1, R d
     }
 }
 
+// per-mark energy of the sampler: the legacy remap -2*sigmoid(c*p + b) + 1 == -tanh((c*p + b) / 2) with the fast exponential
+// (absolute error < 2e-7, far inside the 1e-5 parity budget; the exact float32 sequence of the reference is kept in
+// legacy_remap_f32 for the parity entry points)
 __device__ __forceinline__ float mark_energy_f32(const ModelDev &m, int i, float p) {
-    if (m.setup == MPP_SETUP_LEGACY) return m.premapped ? p : legacy_remap_f32(p, m.coef[i], m.icpt[i]);
-    return m.premapped ? p : -p;
+    if (m.premapped) return p;
+    if (m.setup != MPP_SETUP_LEGACY) return -p;
+    const float z = fmaf(p, m.coef[i], m.icpt[i]);
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(-z));
 }
 
 // det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): one coalesced
 // 128-byte row per mark (lane = class) + one 4-byte gather, all independent -> a single memory round trip.
 template <typename R>
-__device__ __forceinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
+__device__ __noinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
     const float v0 = __ldg(mark_row(c, 0, x, y) + lane), v1 = __ldg(mark_row(c, 1, x, y) + lane), v2 = __ldg(mark_row(c, 2, x, y) + lane);
     const float d = __ldg(c.det + (size_t)x * c.W + y);
     const float s0 = warp_sum(v0), s1 = warp_sum(v1), s2 = warp_sum(v2);
     const float p0 = __shfl_sync(MPP_FULL, v0, cls_of(cls, 0)), p1 = __shfl_sync(MPP_FULL, v1, cls_of(cls, 1)),
                 p2 = __shfl_sync(MPP_FULL, v2, cls_of(cls, 2));
     *detv = d;
-    pn[0] = p0 / s0; pn[1] = p1 / s1; pn[2] = p2 / s2;
+    pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
     dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
 }
 
@@ -251,6 +256,14 @@ __device__ R delta_brute(const ModelDev &m, const WinState<R> &w, int r, bool ha
     return acc;
 }
 
+// out-of-line copies of the two most replicated warp primitives of the sampler (instruction-cache footprint: with many
+// windows resident per SM the kernel is instruction-fetch bound, not issue bound)
+__device__ __noinline__ int warp_pick_ni(float w, float u, int lane, float *total_out) { return warp_pick(w, u, lane, total_out); }
+__device__ __noinline__ void philox2(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, uint4 *q0, uint4 *q1) {
+    Philox rng(seed, c1, c2, c3);
+    *q0 = rng.next(); *q1 = rng.next();
+}
+
 __device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float *n0, float *n1) {
     const float u1 = u01f(a), u2 = u01f(b);
     const float r = sqrtf(-2.0f * __logf(u1));
@@ -293,8 +306,8 @@ struct Eval {  // outcome of evaluating one proposal (warp-uniform)
 template <typename R, bool DBG>
 __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
                                   float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff) {
-    Philox rng(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u);
-    const uint4 q0 = rng.next(), q1 = rng.next();
+    uint4 q0, q1;
+    philox2(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u, &q0, &q1);
     const ModelDev &m = c.m;
     const int nc = w.n_win;
     e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false;
@@ -338,18 +351,18 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     }
     case 2: {  // data-driven birth in the window
         if (!(w.win_mass > 0.0)) { valid = false; break; }
-        const int row = warp_pick(lane < wx ? w.row_mass[lane] : 0.f, u01f(q0.z), lane, nullptr);
+        const int row = warp_pick_ni(lane < wx ? w.row_mass[lane] : 0.f, u01f(q0.z), lane, nullptr);
         const float dv = lane < wy ? __ldg(c.det + (size_t)(w.x0 + row) * c.W + w.y0 + lane) : 0.f;
-        const int col = warp_pick(dv, u01f(q0.w), lane, nullptr);
+        const int col = warp_pick_ni(dv, u01f(q0.w), lane, nullptr);
         a.x = w.x0 + row; a.y = w.y0 + col;
         const float v0 = __ldg(mark_row(c, 0, a.x, a.y) + lane), v1 = __ldg(mark_row(c, 1, a.x, a.y) + lane), v2 = __ldg(mark_row(c, 2, a.x, a.y) + lane);
         float s0, s1, s2;
-        const int c0 = warp_pick(v0, u01f(q1.x), lane, &s0), c1 = warp_pick(v1, u01f(q1.y), lane, &s1), c2 = warp_pick(v2, u01f(q1.z), lane, &s2);
+        const int c0 = warp_pick_ni(v0, u01f(q1.x), lane, &s0), c1 = warp_pick_ni(v1, u01f(q1.y), lane, &s1), c2 = warp_pick_ni(v2, u01f(q1.z), lane, &s2);
         const float p0 = __shfl_sync(MPP_FULL, v0, c0), p1 = __shfl_sync(MPP_FULL, v1, c1), p2 = __shfl_sync(MPP_FULL, v2, c2);
         a.cls = pack_cls(c0, c1, c2);
         a.size = mark_edge<R>(0, c0); a.ratio = mark_edge<R>(1, c1); a.angle = mark_edge<R>(2, c2);
         a.detv = __shfl_sync(MPP_FULL, dv, col);
-        pn[0] = p0 / s0; pn[1] = p1 / s1; pn[2] = p2 / s2;
+        pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
         dm[0] = mark_energy_f32(m, 0, p0); dm[1] = mark_energy_f32(m, 1, p1); dm[2] = mark_energy_f32(m, 2, p2);
         const float fwd = pk_of(w, 2, nc) * dens_of(w, a.detv, pn[0], pn[1], pn[2]) / w.lam_data;
         const float bwd = pk_of(w, 3, nc + 1) / (float)(nc + 1);
@@ -382,10 +395,10 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         float rs = 0.f;
         if (lane < X1 - X0) rs = (float)(c.rowcum[(size_t)(X0 + lane) * pitch + Y1] - c.rowcum[(size_t)(X0 + lane) * pitch + Y0]);
         float tot_s;
-        const int row = warp_pick(rs, u01f(q0.z), lane, &tot_s);
+        const int row = warp_pick_ni(rs, u01f(q0.z), lane, &tot_s);
         if (!(tot_s > 0.f)) { valid = false; break; }
         const float dv = lane < Y1 - Y0 ? __ldg(c.det + (size_t)(X0 + row) * c.W + Y0 + lane) : 0.f;
-        const int col = warp_pick(dv, u01f(q0.w), lane, nullptr);
+        const int col = warp_pick_ni(dv, u01f(q0.w), lane, nullptr);
         const int ex = X0 + row, ey = Y0 + col;
         if (ex < w.x0 || ex >= w.x1 || ey < w.y0 || ey >= w.y1) { valid = false; break; }
         a.x = ex; a.y = ey; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
@@ -417,7 +430,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             ncls = value_to_class<R>(pid, nv);
             s = warp_sum(v);
         } else {
-            ncls = warp_pick(v, u01f(q0.w), lane, &s);
+            ncls = warp_pick_ni(v, u01f(q0.w), lane, &s);
             nv = mark_edge<R>(pid, ncls);
             const float pf = __shfl_sync(MPP_FULL, v, ncls) / s, pb = __shfl_sync(MPP_FULL, v, ocls) / s;
             log_ratio = __logf(pb + W2_EPS) - __logf(pf + W2_EPS);  // p_kernel / n cancel
@@ -442,10 +455,11 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
         const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
         a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+        float fs, fc;
         if (r >= 0 && a.angle == w.angle[r]) {
             a.ca = w.ca[r]; a.sa = w.sa[r];
         } else {
-            r_sincos(a.angle, &a.sa, &a.ca);
+            __sincosf((float)a.angle, &fs, &fc); a.sa = (R)fs; a.ca = (R)fc;
         }
         // capacity of the destination storage cell (MPP_CELL_CAPACITY slots)
         const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
