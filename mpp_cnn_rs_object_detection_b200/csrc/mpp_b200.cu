@@ -26,6 +26,7 @@ struct mpp_ctx {
     void *d_recs = nullptr;
     double *d_cell_cdf = nullptr;
     double *d_rowcum = nullptr;         // [H][W+1] row prefix sums of det
+    float *d_marksum = nullptr;         // [3][H][W] class sums of the mark rows
     int *d_scan = nullptr;              // [ncell + 1] exclusive prefix of per-cell populations
     int *d_nobj = nullptr;
     int *d_rowcount = nullptr;          // [nx] objects per row of cells (global uniform pick)
@@ -65,6 +66,7 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.det = h->det; c.marks = h->marks; c.det_sum = h->det_sum;
     c.cell_cdf = h->d_cell_cdf;
     c.rowcum = h->d_rowcum;
+    c.marksum = h->d_marksum;
     c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
     c.m = h->m; c.k = h->k;
     return c;
@@ -119,6 +121,21 @@ __global__ void k_row_prefix(const float *__restrict__ det, int H, int W, double
         if (b + lane < W) dst[b + lane + 1] = base + incl;
         base += __shfl_sync(MPP_FULL, incl, 31);
     }
+}
+
+// K5c: class sums of the mark rows: one warp per 32 consecutive (mark, pixel) rows, coalesced 128-byte row reads
+__global__ void k_mark_sums(const float *__restrict__ marks, size_t n_rows, float *__restrict__ out) {
+    const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const size_t r0 = warp * 32;
+    float mine = 0.f;
+    for (int k = 0; k < 32; ++k) {
+        const size_t r = r0 + k;
+        if (r >= n_rows) break;
+        const float s = warp_sum(__ldg(marks + r * MPP_N_CLASSES + lane));
+        if (lane == k) mine = s;
+    }
+    if (r0 + lane < n_rows) out[r0 + lane] = mine;
 }
 
 // single-block inclusive scan of doubles in place (ncell <= a few 1e5)
@@ -853,6 +870,7 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_recs, rec * (size_t)h->ncell * MPP_CELL_CAPACITY));
     CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * h->ncell));
     CUDA_TRY(cudaMalloc(&h->d_rowcum, sizeof(double) * (size_t)height * ((size_t)width + 1)));
+    CUDA_TRY(cudaMalloc(&h->d_marksum, sizeof(float) * 3 * (size_t)height * (size_t)width));
     CUDA_TRY(cudaMalloc(&h->d_scan, sizeof(int) * (h->ncell + 1)));
     CUDA_TRY(cudaMalloc(&h->d_nobj, sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->d_rowcount, sizeof(int) * h->nx));
@@ -888,7 +906,7 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     if (!h) return MPP_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
+    cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_marksum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
     cudaFree(h->d_rowcount); cudaFree(h->d_plan); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
@@ -921,6 +939,10 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
     k_cell_mass<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->ny, h->ncell, h->d_cell_cdf);
     k_scan_double<<<1, 1024, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
     k_row_prefix<<<(h->H + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->d_rowcum);
+    {
+        const size_t n_rows = (size_t)3 * h->H * h->W, n_warps = (n_rows + 31) / 32;
+        k_mark_sums<<<(unsigned)((n_warps + 7) / 8), 256, 0, h->stream>>>(marks, n_rows, h->d_marksum);
+    }
     CUDA_TRY(cudaGetLastError());
     if (det_sum > 0.0) {
         h->det_sum = (float)det_sum;
@@ -1283,7 +1305,7 @@ static uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-template <typename R, int NW, bool DBG>
+template <typename R, int NW, bool DBG, bool SIMT = false>
 static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp, uint64_t seed,
                                  uint64_t sweep_id, float *dbg) {
     const uint32_t uid_base = h->window_uid_next;
@@ -1292,16 +1314,16 @@ static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj,
     const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_sweep2<R, NW, DBG><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id,
+    k_sweep2<R, NW, DBG, SIMT><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id,
                                                                   uid_base, dbg);
     return cudaGetLastError();
 }
 
-template <typename R, int NW, bool DBG>
+template <typename R, int NW, bool DBG, bool SIMT = false>
 static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, double alpha_t, double t_target, uint64_t seed,
                            uint64_t sweep_offset, float *dbg) {
     const int S = n_sweeps;
@@ -1346,8 +1368,8 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        CUDA_TRY(cudaFuncSetAttribute(k_windows_dataflow<R, NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_windows_dataflow<R, NW, DBG>, 32 * NW, smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_windows_dataflow<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_windows_dataflow<R, NW, DBG, SIMT>, 32 * NW, smem));
         if (blocks_per_sm < 1) return fail(MPP_ERR_CUDA, "k_windows_dataflow does not fit on an SM");
     }
     // persistent grid: never more CTAs than fit on the device (only CTAs that are running claim tasks, so the in-order
@@ -1355,9 +1377,10 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     // so that small scenes leave room for other contexts' kernels running concurrently on other streams (waiting CTAs
     // occupy SM slots: 32 tiles of 512^2 ran at 46 M proposals/s with two colour classes of CTAs each, 103 M/s with half a class)
     const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
-    static const int cap_x4 = getenv("MPP_GRID_CAP_X4") ? atoi(getenv("MPP_GRID_CAP_X4")) : 2;  // grid <= cap/4 colour classes + 8
+    static const int cap_x4 = SIMT ? (getenv("MPP_GRID_CAP_X4_SIMT") ? atoi(getenv("MPP_GRID_CAP_X4_SIMT")) : 8)
+                                   : (getenv("MPP_GRID_CAP_X4") ? atoi(getenv("MPP_GRID_CAP_X4")) : 2);  // grid <= cap/4 colour classes + 8
     const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_x4 * per_colour / 4 + 8));
-    k_windows_dataflow<R, NW, DBG><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
+    k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
     return MPP_OK;
 }
@@ -1366,7 +1389,8 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
                                uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host, float *debug_maxdiff) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_windows: set maps, model and kernels first");
     if (n_sweeps < 0 || per_visit < 1 || per_visit > 64 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 64)");
-    if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 1, 2, 4 or 8");
+    if (n_warps != 0 && n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8)
+        return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 0 (lane-per-proposal mode), 1, 2, 4 or 8");
     if (schedule != 0 && schedule != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows: schedule must be 0 (colour barriers) or 1 (dataflow)");
     if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
     if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_windows: the window sampler is float32 only (use mpp_run_chain / mpp_replay for float64)");
@@ -1377,6 +1401,9 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
         ? launch_dataflow<float, NWV, true>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff) \
         : launch_dataflow<float, NWV, false>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff))
         switch (n_warps) {
+        case 0: rc = debug_maxdiff ? launch_dataflow<float, 1, true, true>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff)
+                                   : launch_dataflow<float, 1, false, true>(h, n_sweeps, per_visit, t0, alpha_t, t_target, seed, sweep_offset, debug_maxdiff);
+                break;
         case 1: rc = MPP_LAUNCH_D(1); break;
         case 2: rc = MPP_LAUNCH_D(2); break;
         case 4: rc = MPP_LAUNCH_D(4); break;
@@ -1402,6 +1429,9 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
         ? launch_sweep2<float, NWV, true>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff) \
         : launch_sweep2<float, NWV, false>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff))
                 switch (n_warps) {
+                case 0: e = debug_maxdiff ? launch_sweep2<float, 1, true, true>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff)
+                                          : launch_sweep2<float, 1, false, true>(h, ci, cj, n_wi, n_wj, ox, oy, per_visit, (float)temp, seed, sweep_id, debug_maxdiff);
+                        break;
                 case 1: e = MPP_LAUNCH_W(1); break;
                 case 2: e = MPP_LAUNCH_W(2); break;
                 case 4: e = MPP_LAUNCH_W(4); break;
@@ -1421,7 +1451,7 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_window_rows: set maps, model and kernels first");
     if (per_visit < 1 || per_visit > 64 || !(temperature > 0.0) || ci < 0 || ci > 2 || row_lo > row_hi)
         return fail(MPP_ERR_INVALID, "mpp_run_window_rows: bad arguments");
-    if (n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: n_warps must be 1, 2, 4 or 8");
+    if (n_warps != 0 && n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: n_warps must be 0, 1, 2, 4 or 8");
     if (h->m.setup == MPP_SETUP_TOY || h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_window_rows: float32 map-driven model only");
     CUDA_TRY(cudaSetDevice(h->device));
     const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
@@ -1439,6 +1469,7 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
         if (n_wj == 0) continue;
         cudaError_t e;
         switch (n_warps) {
+        case 0: e = launch_sweep2<float, 1, false, true>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
         case 1: e = launch_sweep2<float, 1, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
         case 2: e = launch_sweep2<float, 2, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;
         case 4: e = launch_sweep2<float, 4, false>(h, first, cj, count, n_wj, ox, oy, per_visit, (float)temperature, seed, sweep_id, nullptr); break;

@@ -49,6 +49,7 @@ struct WinState {
     short aov[W2_K], aal[W2_K], aov2[W2_K], aal2[W2_K];  // staged indices of the best / second-best partners
     unsigned char flags[W2_K];
     uint32_t order[W2_K];  // staging scratch: handles in canonical order
+    short winlist[W2_K];   // SIMT mode: staged indices of the alive window objects
     // speculation results, one slot per warp
     int res_accept[W2_MAXW], res_eval[W2_MAXW];
 };
@@ -587,9 +588,401 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
     __syncwarp();
 }
 
+// ================================================================================================ SIMT mode
+// Lane-per-proposal evaluation: ONE warp per window evaluates 32 consecutive proposals of the chain at once, each lane
+// running a whole proposal (draw, map gathers, Delta-energy over the staged objects, Green ratio) by itself.  The first
+// accepted lane is committed (warp-cooperatively), the later ones are discarded and re-drawn: same "speculative moves"
+// semantics as the warp-per-proposal mode, but a window now costs one warp instead of up to eight, every instruction is
+// fetched once for 32 proposals, and the loops over the staged objects read shared memory by broadcast.
+
+// inverse-CDF pick over n <= 32 consecutive floats in global memory: first k with cumulative sum > target.  All the loads
+// are issued before the scan (independent loads, one memory round trip) instead of one dependent load per step.
+__device__ __forceinline__ int scan32(const float *v, int n, float target, float *picked) {
+    float acc = 0.f, lastv = 0.f;
+    int last = 0;
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const float x = v[k];
+        if (!done && k < n && x > 0.f) { last = k; lastv = x; acc += x; done = acc > target; }
+    }
+    *picked = lastv;
+    return last;
+}
+__device__ __forceinline__ int scan_pick_global(const float *row, int n, float target, float *picked) {
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < n ? __ldg(row + k) : 0.f;
+    return scan32(v, n, target, picked);
+}
+// ... over one 128-byte aligned mark row (32 classes): eight 16-byte loads
+__device__ __forceinline__ int scan_pick_row(const float *row, float target, float *picked) {
+    float v[32];
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float4 q = __ldg(r4 + k); v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
+    return scan32(v, 32, target, picked);
+}
+
+// det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): seven independent gathers
+template <typename R>
+__device__ __forceinline__ void gather_pixel(const Ctx<R> &c, int x, int y, uint32_t cls, float *detv, float *pn, float *dm) {
+    const size_t pix = (size_t)x * c.W + y, plane = (size_t)c.H * c.W;
+    const float d = __ldg(c.det + pix);
+    const float p0 = __ldg(mark_row(c, 0, x, y) + cls_of(cls, 0)), p1 = __ldg(mark_row(c, 1, x, y) + cls_of(cls, 1)),
+                p2 = __ldg(mark_row(c, 2, x, y) + cls_of(cls, 2));
+    const float s0 = __ldg(c.marksum + pix), s1 = __ldg(c.marksum + plane + pix), s2 = __ldg(c.marksum + 2 * plane + pix);
+    *detv = d;
+    pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
+    dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
+}
+
+// Delta-energy of removing staged entry r and/or adding `a`, computed by ONE thread over the staged state
+template <typename R>
+__device__ __forceinline__ R delta_lane(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, R *sx, R *sy) {
+    Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    const R rad_a = has_add ? r_sqrt(a.hl * a.hl + a.hw * a.hw) : (R)0;
+    const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
+    R acc = 0, ov_add = 0, al_add = 0;
+    const int n = w.n;
+    for (int k = 0; k < n; ++k) {
+        if (k == r || !(w.flags[k] & W2_ALIVE)) continue;
+        bool touched = false;
+        R ov_a = w.ov1[k], al_a = w.al1[k];
+        const int kx = w.x[k], ky = w.y[k];
+        if (r >= 0) {
+            const int dx = kx - rx, dy = ky - ry;
+            if (dx * dx + dy * dy <= m.max_d2) {
+                touched = true;
+                if (w.aov[k] == r) ov_a = w.ov2[k];
+                if (w.aal[k] == r) al_a = w.al2[k];
+            }
+        }
+        if (has_add) {
+            const int dx = kx - a.x, dy = ky - a.y, d2 = dx * dx + dy * dy;
+            if (d2 <= m.max_d2) {
+                touched = true;
+                if (d2 <= m.ov_d2) { const R o = pair_ov_w(m, w, k, ga, rad_a, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
+                if (d2 <= m.al_d2) { const R al = align_magnitude(geo_w(w, k), ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
+            }
+        }
+        if (touched) acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, w.ov1[k], w.al1[k]);
+    }
+    if (has_add) {
+        Terms<R> t;
+        t.pos = a.pos;
+        shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
+        t.ov = ov_add; t.al = (m.rewarding ? (R)-1 : (R)1) * al_add;
+        t.area = area_prior_fast<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
+        acc += combine_fast(m, t);
+    }
+    if (r >= 0) acc -= f_obj(m, w, r, w.ov1[r], w.al1[r]);
+    return acc;
+}
+
+// brute-force twin of delta_lane (debug): every reduction recomputed from scratch by the same thread
+template <typename R>
+__device__ R delta_lane_brute(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, R *sx, R *sy) {
+    Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    R acc = 0, oadd = 0, aadd = 0;
+    const int n = w.n;
+    for (int k = 0; k < n; ++k) {
+        if (!(w.flags[k] & W2_ALIVE)) continue;
+        R ob = 0, ab = 0, oa = 0, aa = 0;
+        const Geo<R> gk = geo_w(w, k);
+        for (int v = 0; v < n; ++v) {
+            if (v == k || !(w.flags[v] & W2_ALIVE)) continue;
+            const int dx = w.x[v] - gk.x, dy = w.y[v] - gk.y, d2 = dx * dx + dy * dy;
+            if (d2 > m.max_d2) continue;
+            R o = 0, al = 0;
+            if (d2 <= m.ov_d2) o = pair_overlap(m, gk, geo_w(w, v), d2, sx, sy);
+            if (d2 <= m.al_d2) al = align_magnitude(gk, geo_w(w, v), m.rewarding);
+            ob = r_max(ob, o); ab = r_max(ab, al);
+            if (v != r) { oa = r_max(oa, o); aa = r_max(aa, al); }
+        }
+        if (has_add && k != r) {
+            const int dx = a.x - gk.x, dy = a.y - gk.y, d2 = dx * dx + dy * dy;
+            if (d2 <= m.ov_d2) { const R o = pair_overlap(m, gk, ga, d2, sx, sy); oa = r_max(oa, o); oadd = r_max(oadd, o); }
+            if (d2 <= m.al_d2) { const R al = align_magnitude(gk, ga, m.rewarding); aa = r_max(aa, al); aadd = r_max(aadd, al); }
+        }
+        if (k == r) acc -= f_obj(m, w, k, ob, ab);
+        else if (oa != ob || aa != ab) acc += f_obj(m, w, k, oa, aa) - f_obj(m, w, k, ob, ab);
+    }
+    if (has_add) {
+        Terms<R> t;
+        t.pos = a.pos;
+        shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
+        t.ov = oadd; t.al = (m.rewarding ? (R)-1 : (R)1) * aadd;
+        t.area = area_prior_fast<R>(m, a.hl, a.hw);
+        t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
+        acc += combine_fast(m, t);
+    }
+    return acc;
+}
+
+// Proposal number `it` of this window's chain, drawn and evaluated by the calling THREAD against the staged state.
+template <typename R, bool DBG>
+__device__ __forceinline__ void evaluate_lane(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it, float temp,
+                              R *sx, R *sy, Eval<R> *e, float *dbg_maxdiff) {
+    Philox rng(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x51000000u);
+    const uint4 q0 = rng.next(), q1 = rng.next();
+    const ModelDev &m = c.m;
+    const int nc = w.n_win;
+    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false;
+    int kernel;
+    {
+        const float uk = u01f(q0.x);
+        if (nc > 0) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += w.pkf[k]; if (uk < acc) { kernel = k; break; } } }
+        else kernel = uk < w.pk_e0 ? 0 : 2;
+    }
+    e->kernel = kernel;
+    const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
+    int r = -1;
+    if (kernel != 0 && kernel != 2) r = w.winlist[min(nc - 1, (int)(u01f(q0.y) * (float)nc))];
+    e->r = r;
+    Cand<R> &a = e->a;
+    bool valid = true, has_add = false, need_gather = false;
+    float log_ratio = 0.f, aux0 = 0.f, aux1 = 0.f;  // kernel-specific proposal densities gathered in phase 1
+    int pid = 0;
+    // ---- phase 1 (divergent): where / what is proposed
+    switch (kernel) {
+    case 0:
+        a.x = w.x0 + min(wx - 1, (int)(u01f(q0.z) * (float)wx));
+        a.y = w.y0 + min(wy - 1, (int)(u01f(q0.w) * (float)wy));
+        a.size = (R)(u01f(q1.x) * 32.0f); a.ratio = (R)u01f(q1.y); a.angle = (R)(u01f(q1.z) * 3.14159265358979f);
+        a.cls = pack_cls(value_to_class<R>(0, a.size), value_to_class<R>(1, a.ratio), value_to_class<R>(2, a.angle));
+        has_add = true; need_gather = true;
+        break;
+    case 1:
+        break;
+    case 2: {
+        if (!(w.win_mass > 0.0)) { valid = false; break; }
+        float acc = 0.f;
+        const float tr = u01f(q0.z) * (float)w.win_mass;
+        int row = 0;
+        for (int k = 0; k < wx; ++k) { const float v = w.row_mass[k]; if (v > 0.f) { row = k; acc += v; if (acc > tr) break; } }
+        float dv;
+        const int col = scan_pick_global(c.det + (size_t)(w.x0 + row) * c.W + w.y0, wy, u01f(q0.w) * w.row_mass[row], &dv);
+        a.x = w.x0 + row; a.y = w.y0 + col;
+        const size_t pix = (size_t)a.x * c.W + a.y, plane = (size_t)c.H * c.W;
+        float pv;
+        const int c0 = scan_pick_row(mark_row(c, 0, a.x, a.y), u01f(q1.x) * __ldg(c.marksum + pix), &pv);
+        const int c1 = scan_pick_row(mark_row(c, 1, a.x, a.y), u01f(q1.y) * __ldg(c.marksum + plane + pix), &pv);
+        const int c2 = scan_pick_row(mark_row(c, 2, a.x, a.y), u01f(q1.z) * __ldg(c.marksum + 2 * plane + pix), &pv);
+        a.cls = pack_cls(c0, c1, c2);
+        a.size = mark_edge<R>(0, c0); a.ratio = mark_edge<R>(1, c1); a.angle = mark_edge<R>(2, c2);
+        has_add = true; need_gather = true;
+        break;
+    }
+    case 3:
+        if (!(w.win_mass > 0.0)) valid = false;
+        break;
+    case 4: {
+        float d0, d1;
+        box_muller_f(q0.z, q0.w, &d0, &d1);
+        const int nx_ = min(max((int)((float)w.x[r] + d0 * (float)c.k.trl_sigma), 0), c.H - 1);
+        const int ny_ = min(max((int)((float)w.y[r] + d1 * (float)c.k.trl_sigma), 0), c.W - 1);
+        if (nx_ < w.x0 || nx_ >= w.x1 || ny_ < w.y0 || ny_ >= w.y1) { valid = false; break; }
+        a.x = nx_; a.y = ny_; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        has_add = true; need_gather = true;
+        break;
+    }
+    case 5: {
+        const int md = c.k.trl_max_delta;
+        const int X0 = max(0, w.x[r] - md), X1 = min(w.x[r] + md + 1, c.H), Y0 = max(0, w.y[r] - md), Y1 = min(w.y[r] + md + 1, c.W);
+        const size_t pitch = (size_t)c.W + 1;
+        float rs[17], tot_s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            rs[i] = (i < X1 - X0) ? (float)(c.rowcum[(size_t)(X0 + i) * pitch + Y1] - c.rowcum[(size_t)(X0 + i) * pitch + Y0]) : 0.f;
+            tot_s += rs[i];
+        }
+        if (!(tot_s > 0.f)) { valid = false; break; }
+        int row = 0;
+        {
+            float acc = 0.f;
+            const float tr = u01f(q0.z) * tot_s;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) if (rs[i] > 0.f && acc <= tr) { row = i; acc += rs[i]; }
+        }
+        float dv;
+        const float rowtot = (float)(c.rowcum[(size_t)(X0 + row) * pitch + Y1] - c.rowcum[(size_t)(X0 + row) * pitch + Y0]);
+        const int col = scan_pick_global(c.det + (size_t)(X0 + row) * c.W + Y0, Y1 - Y0, u01f(q0.w) * rowtot, &dv);
+        const int ex = X0 + row, ey = Y0 + col;
+        if (ex < w.x0 || ex >= w.x1 || ey < w.y0 || ey >= w.y1) { valid = false; break; }
+        a.x = ex; a.y = ey; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        const int BX0 = max(0, ex - md), BX1 = min(ex + md + 1, c.H), BY0 = max(0, ey - md), BY1 = min(ey + md + 1, c.W);
+        float tot_e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 17; ++i)
+            if (i < BX1 - BX0) tot_e += (float)(c.rowcum[(size_t)(BX0 + i) * pitch + BY1] - c.rowcum[(size_t)(BX0 + i) * pitch + BY0]);
+        aux0 = tot_s; aux1 = tot_e;
+        has_add = true; need_gather = true;
+        break;
+    }
+    default: {  // 6: gaussian mark transform, 7: data-driven mark transform
+        pid = min(2, (int)(u01f(q0.z) * 3.0f));
+        const size_t pix = (size_t)w.x[r] * c.W + w.y[r], plane = (size_t)c.H * c.W;
+        const float *row = mark_row(c, pid, w.x[r], w.y[r]);
+        const float s = __ldg(c.marksum + (size_t)pid * plane + pix);
+        const int ocls = cls_of(w.cls[r], pid);
+        int ncls;
+        R nv;
+        float pnew;
+        if (kernel == 6) {
+            float d0, d1;
+            box_muller_f(q0.w, q1.x, &d0, &d1);
+            nv = (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r])) + (R)(d0 * (float)c.k.trf_sigma[pid]);
+            const R vmax = (R)mark_vmax(pid);
+            if (pid == 2) { nv = nv - r_floor(nv / vmax) * vmax; if (!(nv < vmax) || nv < 0) nv = 0; }
+            else nv = r_min(r_max(nv, (R)0), vmax);
+            ncls = value_to_class<R>(pid, nv);
+            pnew = __ldg(row + ncls);
+        } else {
+            ncls = scan_pick_row(row, u01f(q0.w) * s, &pnew);
+            nv = mark_edge<R>(pid, ncls);
+            const float pb = __ldg(row + ocls);
+            log_ratio = __logf(__fdividef(pb, s) + W2_EPS) - __logf(__fdividef(pnew, s) + W2_EPS);  // p_kernel / n cancel
+        }
+        a.x = w.x[r]; a.y = w.y[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        if (pid == 0) a.size = nv; else if (pid == 1) a.ratio = nv; else a.angle = nv;
+        a.cls = (w.cls[r] & ~(0xffu << (8 * pid))) | ((uint32_t)ncls << (8 * pid));
+        a.detv = w.detv[r];
+        a.pn0 = w.pn0[r]; a.pn1 = w.pn1[r]; a.pn2 = w.pn2[r];
+        a.dm0 = w.dm0[r]; a.dm1 = w.dm1[r]; a.dm2 = w.dm2[r];
+        const float pnn = __fdividef(pnew, s);
+        const R dmn = (R)mark_energy_f32(m, pid, pnew);
+        if (pid == 0) { a.pn0 = pnn; a.dm0 = dmn; } else if (pid == 1) { a.pn1 = pnn; a.dm1 = dmn; } else { a.pn2 = pnn; a.dm2 = dmn; }
+        has_add = true;
+        break;
+    }
+    }
+    if (!valid) return;
+    // ---- phase 2 (common): maps at the proposed pixel, geometry
+    if (need_gather) {
+        float pn[3], dm[3];
+        gather_pixel(c, a.x, a.y, a.cls, &a.detv, pn, dm);
+        a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
+        a.dm0 = (R)dm[0]; a.dm1 = (R)dm[1]; a.dm2 = (R)dm[2];
+    }
+    if (has_add) {
+        a.pos = (R)position_energy_f32(a.detv, m.pos_thr);
+        const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
+        a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+        if (r >= 0 && a.angle == w.angle[r]) { a.ca = w.ca[r]; a.sa = w.sa[r]; }
+        else { float fs, fc; __sincosf((float)a.angle, &fs, &fc); a.sa = (R)fs; a.ca = (R)fc; }
+        const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
+        uint32_t dmk = w.cmask[ci];
+        if (r >= 0 && (int)(w.handle[r] >> 5) == w.ccell[ci]) dmk &= ~(1u << (w.handle[r] & 31));
+        if (dmk == 0xffffffffu) return;
+    }
+    // ---- phase 3: proposal ratio log(bwd) - log(fwd)
+    switch (kernel) {
+    case 0: log_ratio = __logf(pk_of(w, 1, nc + 1) / (float)(nc + 1) + W2_EPS) - __logf(pk_of(w, 0, nc) / w.lam_unif + W2_EPS); break;
+    case 1: log_ratio = __logf(pk_of(w, 0, nc - 1) / w.lam_unif + W2_EPS) - __logf(pk_of(w, 1, nc) / (float)nc + W2_EPS); break;
+    case 2: log_ratio = __logf(pk_of(w, 3, nc + 1) / (float)(nc + 1) + W2_EPS) -
+                        __logf(pk_of(w, 2, nc) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2) / w.lam_data + W2_EPS); break;
+    case 3: log_ratio = __logf(pk_of(w, 2, nc - 1) * dens_of(w, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]) / w.lam_data + W2_EPS) -
+                        __logf(pk_of(w, 3, nc) / (float)nc + W2_EPS); break;
+    case 5: log_ratio = __logf(__fdividef(w.detv[r], aux1) + W2_EPS) - __logf(__fdividef(a.detv, aux0) + W2_EPS); break;
+    default: break;  // 4, 6: symmetric; 7: set in phase 1
+    }
+    // ---- phase 4: Delta-energy and the accept test
+    e->has_add = has_add;
+    const R de = delta_lane(m, w, r, has_add, a, sx, sy);
+    if (DBG && dbg_maxdiff) {
+        const float diff = fabsf((float)(de - delta_lane_brute(m, w, r, has_add, a, sx, sy)));
+        atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
+    }
+    const float la = -(float)de / temp + log_ratio;
+    e->evaluated = true;
+    e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
+}
+
+// pair values between every staged entry and the object about to be added (what delta_staged stashes in the warp mode)
+template <typename R>
+__device__ __forceinline__ void fill_pairs(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy,
+                                           R *po, R *pa) {
+    if (!has_add) return;
+    Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+    const R rad_a = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+    const int n = w.n;
+    for (int k = lane; k < n; k += 32) {
+        R o = 0, al = 0;
+        if (k != r && (w.flags[k] & W2_ALIVE)) {
+            const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
+            if (d2 <= m.ov_d2) o = pair_ov_w(m, w, k, ga, rad_a, d2, sx, sy);
+            if (d2 <= m.al_d2) al = align_magnitude(geo_w(w, k), ga, m.rewarding);
+        }
+        po[k] = o; pa[k] = al;
+    }
+    __syncwarp();
+}
+
+// staged indices of the alive window objects, ascending (the order proposals pick from)
+template <typename R>
+__device__ __forceinline__ void rebuild_winlist(WinState<R> &w, int lane) {
+    const int n = w.n;
+    int cnt = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int k = b + lane;
+        const bool in = k < n && (w.flags[k] & (W2_ALIVE | W2_WIN)) == (W2_ALIVE | W2_WIN);
+        const uint32_t bal = __ballot_sync(MPP_FULL, in);
+        if (in) w.winlist[cnt + __popc(bal & ((1u << lane) - 1))] = (short)k;
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+}
+
+template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(MPP_FULL, v, src); }
+
+// the speculative rounds of one visit in SIMT mode (one warp)
+template <typename R, bool DBG>
+__device__ __forceinline__ void simt_rounds(const Ctx<R> &c, WinState<R> &w, int per_visit, float temp, uint64_t seed, uint32_t win_id, uint64_t sweep_id,
+                            int lane, R *sx, R *sy, R *po, R *pa, float *dbg_maxdiff) {
+    rebuild_winlist(w, lane);
+    int it = 0;
+    while (it < per_visit) {
+        Eval<R> e;
+        const int mine = it + lane;
+        e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.kernel = 0;
+        if (mine < per_visit) evaluate_lane<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, sx, sy, &e, dbg_maxdiff);
+        __syncwarp();
+        const uint32_t bal = __ballot_sync(MPP_FULL, e.accept);
+        const int first = bal ? __ffs(bal) - 1 : 32;
+        const int used = min(first + 1, min(32, per_visit - it));
+        const uint32_t evb = __ballot_sync(MPP_FULL, e.evaluated && lane < used);
+        if (lane == 0) { w.n_eval += __popc(evb); w.n_done += used; }
+        if (first < 32) {
+            Eval<R> g;  // the accepted proposal, broadcast from its lane
+            g.kernel = bcast(e.kernel, first); g.r = bcast(e.r, first); g.has_add = bcast((int)e.has_add, first) != 0;
+            g.evaluated = true; g.accept = true;
+            g.a.x = bcast(e.a.x, first); g.a.y = bcast(e.a.y, first); g.a.cls = bcast(e.a.cls, first);
+            g.a.size = bcast(e.a.size, first); g.a.ratio = bcast(e.a.ratio, first); g.a.angle = bcast(e.a.angle, first);
+            g.a.hl = bcast(e.a.hl, first); g.a.hw = bcast(e.a.hw, first); g.a.ca = bcast(e.a.ca, first); g.a.sa = bcast(e.a.sa, first);
+            g.a.pos = bcast(e.a.pos, first); g.a.dm0 = bcast(e.a.dm0, first); g.a.dm1 = bcast(e.a.dm1, first); g.a.dm2 = bcast(e.a.dm2, first);
+            g.a.detv = bcast(e.a.detv, first); g.a.pn0 = bcast(e.a.pn0, first); g.a.pn1 = bcast(e.a.pn1, first); g.a.pn2 = bcast(e.a.pn2, first);
+            if (lane == 0) {
+                w.n_acc += 1;
+                if (g.has_add && g.r < 0) w.n_birth += 1;
+                if (!g.has_add && g.r >= 0) w.n_death += 1;
+            }
+            if (w.n >= W2_K && g.has_add && g.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
+            else {
+                fill_pairs(c.m, w, g.r, g.has_add, g.a, lane, sx, sy, po, pa);
+                commit_proposal(c, w, g, it + first, lane, sx, sy, po, pa);
+                rebuild_winlist(w, lane);
+            }
+        }
+        __syncwarp();
+        it += used;
+    }
+}
+
 // One visit of window (wi, wj) of the grid shifted by (ox, oy): staging, `per_visit` proposals, publication.
 // `uid_first` is the uid of the first object this visit may create.  Must be called by the whole CTA.
-template <typename R, int NW, bool DBG>
+template <typename R, int NW, bool DBG, bool SIMT = false>
 __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi, int wj, int ox, int oy, int per_visit, float temp,
                              uint64_t seed, uint64_t sweep_id, uint32_t uid_first, float *dbg_maxdiff) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -720,6 +1113,17 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 
     // ------------------------------------------------------------------ speculative proposal rounds
     int it = 0;
+    if (SIMT) {  // lane-per-proposal mode: the CTA is one warp
+#ifdef MPP_TRACE
+        const long long t_s = clock64();
+#endif
+        simt_rounds<R, DBG>(c, w, per_visit, temp, seed, win_id, sweep_id, lane, sx, sy, po, pa, dbg_maxdiff);
+        it = per_visit;
+        __syncthreads();
+#ifdef MPP_TRACE
+        t_eval = clock64() - t_s; n_rounds = w.n_acc + 1;
+#endif
+    }
     while (it < per_visit) {
         Eval<R> e;
         const int mine = it + warp;
@@ -779,7 +1183,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 }
 
 // ---- schedule 0: one launch per colour class (global barrier between colours) ------------------------
-template <typename R, int NW, bool DBG>
+template <typename R, int NW, bool DBG, bool SIMT>
 __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp,
                                                    uint64_t seed, uint64_t sweep_id, uint32_t uid_base, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -787,7 +1191,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
     R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
     const int a = blockIdx.x;
     if (a >= n_wi * n_wj) return;
-    window_visit<R, NW, DBG>(c, w, scratch, ci + 3 * (a / n_wj), cj + 3 * (a % n_wj), ox, oy, per_visit, temp, seed, sweep_id,
+    window_visit<R, NW, DBG, SIMT>(c, w, scratch, ci + 3 * (a / n_wj), cj + 3 * (a % n_wj), ox, oy, per_visit, temp, seed, sweep_id,
                              uid_base + (uint32_t)a * (uint32_t)per_visit, dbg_maxdiff);
 }
 
@@ -819,7 +1223,7 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 #ifndef MPP_DF_MIN_BLOCKS
 #define MPP_DF_MIN_BLOCKS 2
 #endif
-template <typename R, int NW, bool DBG>
+template <typename R, int NW, bool DBG, bool SIMT>
 __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
                                                              uint32_t uid_base, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -873,7 +1277,7 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
             }
         }
         __syncthreads();
-        window_visit<R, NW, DBG>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
+        window_visit<R, NW, DBG, SIMT>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
                                  uid_base + (uint32_t)t * (uint32_t)per_visit, dbg_maxdiff);
         __syncthreads();
         if (threadIdx.x == 0) {

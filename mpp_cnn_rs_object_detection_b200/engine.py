@@ -361,7 +361,7 @@ class Engine:
                     t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True, debug: bool = False,
                     schedule: str = "dataflow"):
         """Production parallel sampler (mpp_run_windows): shifted 32-px windows, shared-memory resident visits, speculative
-        evaluation by `n_warps` warps.  Returns [proposals, accepted, births, deaths, evaluated, 0, 0, 0] (+ the largest
+        evaluation by `n_warps` warps (1, 2, 4, 8: one proposal per warp; 0: one warp per window, one proposal per lane).  Returns [proposals, accepted, births, deaths, evaluated, 0, 0, 0] (+ the largest
         |fast - brute-force| Delta-energy difference when debug=True)."""
         cnt = (C.c_ulonglong * 8)()
         dbg = torch.zeros(1, dtype=torch.float32, device=self.device) if debug else None

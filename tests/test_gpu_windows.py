@@ -18,11 +18,14 @@ def _scene(cfg, seed=5, shape=(192, 224), n_rect=60):
     return objs, det, marks, eng
 
 
+@pytest.mark.parametrize("n_warps", [4, 0])
 @pytest.mark.parametrize("cfg,n_rect,temp", [("legacy", 60, 0.03), ("nocalib", 60, 0.03), ("legacy", 170, 0.02), ("nocalib", 170, 0.01)])
-def test_fast_delta_equals_brute_force(cfg, n_rect, temp):
-    """n_rect=170 on 192x224 is ~4x the benchmark density: many partners within reach, overlaps and second-best partners."""
+def test_fast_delta_equals_brute_force(cfg, n_rect, temp, n_warps):
+    """n_rect=170 on 192x224 is ~4x the benchmark density: many partners within reach, overlaps and second-best partners.
+    n_warps=0 is the lane-per-proposal mode."""
     objs, det, marks, eng = _scene(cfg, n_rect=n_rect)
-    cnt, maxdiff = eng.run_windows(40, proposals_per_visit=12, n_warps=4, t0=temp, seed=3, debug=True, schedule="colours" if n_rect < 100 else "dataflow")
+    cnt, maxdiff = eng.run_windows(40, proposals_per_visit=12 if n_warps else 40, n_warps=n_warps, t0=temp, seed=3, debug=True,
+                                   schedule="colours" if n_rect < 100 else "dataflow")
     assert cnt[0] > 0 and cnt[4] > 0 and cnt[1] > 0
     assert maxdiff < 2e-5, maxdiff
     assert len(eng) == len(objs) + cnt[2] - cnt[3]
@@ -67,7 +70,28 @@ def _batch_se(x, nb=20):
     return x.mean(), b.std(ddof=1) / np.sqrt(nb)
 
 
-def test_stationary_distribution_matches_sequential_chain():
+def test_lane_mode_is_schedule_independent_and_consistent():
+    """Lane-per-proposal mode: same chain under both schedules; the records it writes are consistent."""
+    from tests.gpu_util import make_engine
+    finals = []
+    for schedule in ("colours", "dataflow"):
+        objs, det, marks, eng = _scene("legacy")
+        cnt = eng.run_windows(25, proposals_per_visit=40, n_warps=0, t0=0.03, seed=9, schedule=schedule)
+        h, xy, mk, uid = eng.read_objects()
+        order = np.lexsort((xy[:, 1], xy[:, 0]))
+        finals.append((cnt[:5], xy[order], mk[order]))
+        assert cnt[1] > 0 and len(eng) == len(objs) + cnt[2] - cnt[3]
+    assert finals[0][0] == finals[1][0]
+    np.testing.assert_array_equal(finals[0][1], finals[1][1])
+    np.testing.assert_array_equal(finals[0][2], finals[1][2])
+    vec, comb, raw, tot = eng.energy_vectors(h)
+    fresh = make_engine("legacy", det, marks, "fp32")
+    vec2, comb2, _, _ = fresh.energy_vectors(fresh.add_objects(xy, mk))
+    np.testing.assert_allclose(vec, vec2, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_warps", [2, 0])
+def test_stationary_distribution_matches_sequential_chain(n_warps):
     from mpp_cnn_rs_object_detection_b200 import synth
     from tests.gpu_util import make_engine
     temp = 0.3
@@ -79,13 +103,13 @@ def test_stationary_distribution_matches_sequential_chain():
     mb, sb = _batch_se(trace["n_after"][::10])
     e2 = make_engine("legacy", det, marks, "fp32", intensity=max(1, len(objs)))
     e2.add_objects(objs[:, :2], objs[:, 2:5])
-    e2.run_windows(300, proposals_per_visit=4, n_warps=2, t0=temp, seed=2)
+    e2.run_windows(300, proposals_per_visit=4, n_warps=n_warps, t0=temp, seed=2)
     nc = []
     for s in range(6000):
-        e2.run_windows(1, proposals_per_visit=4, n_warps=2, t0=temp, seed=2, sweep_offset=300 + s, read_counters=False)
+        e2.run_windows(1, proposals_per_visit=4, n_warps=n_warps, t0=temp, seed=2, sweep_offset=300 + s, read_counters=False)
         nc.append(len(e2))
     mc, sc = _batch_se(nc)
-    print(f"\nobject count at T={temp}: device chain {mb:.3f}+-{sb:.3f} | windows {mc:.3f}+-{sc:.3f}")
+    print(f"\nobject count at T={temp}: device chain {mb:.3f}+-{sb:.3f} | windows(n_warps={n_warps}) {mc:.3f}+-{sc:.3f}")
     assert abs(mb - mc) < 5 * np.hypot(sb, sc) + 0.04, (mb, mc)
 
 
