@@ -162,7 +162,6 @@ def cpu_patches(args, device):
     objs, det, marks = synth.make_scene_torch(args.seed, (args.size, args.size), n_rect_for(args), device)
     workers = cb.host_cores()
     # crop on the device, move only the needed patches to the host
-    det_np = None
     patches = []
     h = w = args.size
     for i in range(0, h, cb.PATCH):
@@ -176,7 +175,6 @@ def cpu_patches(args, device):
             o[:, 1] -= j
             patches.append((det[i:i1, j:j1].contiguous().cpu().numpy(),
                             [marks[k, i:i1, j:j1].contiguous().cpu().numpy() for k in range(3)], o))
-    del det_np
     return patches
 
 

@@ -5,8 +5,6 @@ from abc import abstractmethod
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Type, Union
 
-import numpy as np
-
 from .mappings import ValueMapping
 from .shapes import Point, Rectangle
 

@@ -6,11 +6,8 @@ device cell lists, and `ue_per_point` / `pe_per_point` are read-only views built
 from __future__ import annotations
 
 import weakref
-from typing import Dict, Iterable, List, Optional, Set, Union
+from typing import Dict, List, Optional, Set, Union
 
-import numpy as np
-
-from .. import _lib
 from .custom_types import EnergyCombinationModel, Perturbation
 from .device_state import DeviceState, build_layout
 from .energies import PairEnergy, PairEnergyConstructor, UnitEnergy, UnitEnergyConstructor
@@ -125,9 +122,7 @@ class EnergyGraph:
     def _pair_value(self, pe: PairEnergy) -> float:
         st = self._state
         out = st.engine.pair_values(st.handles([pe.point_1]), st.handles([pe.point_2]))[0]
-        kind = self.pe_constructors.index(pe.constructor)
         col = 0 if (self._layout.spec.setup == "toy" or type(pe.constructor).__name__ == "RectangleOverlapEnergy") else 1
-        del kind
         return float(out[col])
 
     def _pair_list(self, u: Point) -> List[PairEnergy]:

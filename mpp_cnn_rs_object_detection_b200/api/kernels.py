@@ -6,7 +6,7 @@ from __future__ import annotations
 
 from abc import abstractmethod
 from copy import copy
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 
@@ -14,7 +14,7 @@ from .. import _lib
 from ..engine import kernel_probabilities
 from .custom_types import ImageWMaps, Perturbation
 from .point_set import PointsSet
-from .shapes import Point, Rectangle
+from .shapes import Rectangle
 
 BASE_KERNEL_WEIGHTS = {  # make_kernels.py:13-24
     "bd_weight": 1, "uniform_bd_weight": 1, "data_bd_weight": 2, "ms_weight": 1, "translation_weight": 1,

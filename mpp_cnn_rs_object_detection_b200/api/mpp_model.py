@@ -12,7 +12,6 @@ Differences from the reference, all on the host side of the hot path:
 from __future__ import annotations
 
 import io
-import json
 import logging
 import os
 import pickle

@@ -131,7 +131,6 @@ class RJMCMC:
         total = self.stopping_condition.max_iter + 1 - self._iter  # StopOnMaxIter runs max_iter + 1 steps (stopping.py:42)
         seed = int(self.rng.integers(0, 2 ** 62))
         alpha = self.alpha_t if self.do_annealing else 1.0
-        names = [k.__class__ for k in self.kernels]
         done = 0
         while done < total:
             # run up to (and including) the next step at which sampling_rule asks for a snapshot
@@ -156,7 +155,6 @@ class RJMCMC:
             done = seg_end
             if self.sampling_rule is not None and self.sampling_rule(self._iter - 1):
                 self._state_log.append(x.copy())
-        del names
 
     def run(self, show_timing=False) -> Tuple[Union[List[EPointsSet], EPointsSet], List[RJMCMCStateSummary]]:
         if self._device_chain_possible() and self.verbose == 0:

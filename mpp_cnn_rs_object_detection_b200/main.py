@@ -45,8 +45,6 @@ def main(argv=None):
     model = mm.MPPModel(config, phase="val", load=True, model_dir=model_dir)
     print("infering on dataset")
     if args.synthetic:
-        import numpy as np
-
         from . import synth
         from .api import ImageWMaps, default_mappings
         h, w = (int(v) for v in args.synthetic.lower().split("x"))
