@@ -202,7 +202,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                   energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
                   iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
                   proposals_per_visit: int = 32, warps_per_window: int = 8, precision: str = "fp32",
-                  reuse_device_maps: bool = True, return_stats: bool = False, _device_maps=None):
+                  reuse_device_maps: bool = True, return_stats: bool = False, _device_maps=None, _defer: bool = False):
     """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
 
     sampler='parallel'   window sampler (mpp_run_windows): max_iter + 1 proposals in total, spread over
@@ -211,7 +211,9 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                          alpha_t ** proposals_per_sweep per sweep).
     sampler='sequential' the reference's one-proposal-at-a-time chain, run on the device.
     reuse_device_maps    False: always upload the maps (no cache keyed on the host arrays).
-    return_stats         True: returns (result, dict of device counters) instead of result."""
+    return_stats         True: returns (result, dict of device counters) instead of result.
+    _defer               (internal, sample_rjmcmc_batch) parallel sampler, single sample: queue the chain and return a function
+                         that waits for it and builds the result, so that the caller can overlap host work with the sampling."""
     if use_split_merge and sampler != "sequential":
         raise NotImplementedError("the optional split / merge kernels run through the step-by-step chain: pass sampler='sequential'")
     unit_energies, pair_energies = energy_setup.make_energies(image_data)
@@ -277,22 +279,25 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                 st.refresh_from_device()
                 points.energy_graph._members = dict.fromkeys(st.handle_of)
                 states.append(points.copy())
-        if return_stats:
-            c = eng.run_windows(0, proposals_per_visit, warps_per_window, t0=max(temp, 1e-30))
-            stats.update(proposals=c[0], accepted=c[1], births=c[2], deaths=c[3], evaluated=c[4])
-        st.refresh_from_device()
-        points.energy_graph._members = dict.fromkeys(st.handle_of)
-        if not states:
-            states = [points]
-        result = [states[-1].points] if num_samples == 1 else [s.points for s in states[-num_samples:]]
+
+        def finish():
+            if return_stats:
+                c = eng.run_windows(0, proposals_per_visit, warps_per_window, t0=max(temp, 1e-30))
+                stats.update(proposals=c[0], accepted=c[1], births=c[2], deaths=c[3], evaluated=c[4], launches=eng.launches)
+            st.refresh_from_device()
+            points.energy_graph._members = dict.fromkeys(st.handle_of)
+            sampled = states if states else [points]
+            res = [sampled[-1].points] if num_samples == 1 else [s.points for s in sampled[-num_samples:]]
+            return (res, stats) if return_stats else res
+
+        if _defer:
+            return finish
+        result = finish()
     else:
         raise ValueError(f"sampler must be 'parallel' or 'sequential', got {sampler!r}")
     end = time.perf_counter()
-    if return_stats:
-        if sampler != "parallel":
-            stats = {"proposals": max_iter + 1, "evaluated": max_iter + 1}
-        stats["launches"] = st.engine.launches
-        result = (result, stats)
+    if return_stats and sampler != "parallel":
+        result = (result, {"proposals": max_iter + 1, "evaluated": max_iter + 1, "launches": st.engine.launches})
     logging.info(f"rjmcmc on image {image_data.name} ran in {end - start:.2f}s ({(end - start) / max(1, max_iter):.1e}s/iter) "
                  f"(int. {intensity} | iter {max_iter} | num_samples {num_samples} | {sampler})")
     return result
@@ -301,7 +306,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
 def sample_rjmcmc_batch(images, rng: np.random.Generator, with_scores: bool = False, **params):
     """sample_rjmcmc over a sequence of images (the role of `_map_to_images(partial(sample_rjmcmc, ...), images)`,
     models/mpp/train_energy_combination/train_utils.py:11-18 and mpp_model.py:250-264) with the host-to-device upload of
-    image i+1 overlapped with the sampling of image i (second CUDA stream, recycled device buffers).  `params` are
+    image i+1 and the host-side read-back of image i-1 overlapped with the sampling of image i (second CUDA stream,
+    recycled device buffers).  `params` are
     sample_rjmcmc's keyword arguments.  Device state is released image by image, so the result is detached: per image a
     list (one entry per sample) of lists of Rectangle; with_scores=True returns (rectangles, Papangelou scores of the last
     sample: exp(+Delta E of removal), mpp_model.py:296-304) per image; return_stats=True appends the counters dict."""
@@ -316,39 +322,52 @@ def sample_rjmcmc_batch(images, rng: np.random.Generator, with_scores: bool = Fa
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def upload(img):
+    def upload(img, first=False):
         unit, pair = energy_setup.make_energies(img)
         layout = build_layout(unit, pair)
-        copy_stream.wait_stream(main)  # the buffers handed out by the pool may still be read by queued kernels
+        if first:  # later hand-outs recycle buffers whose last reader finished before a host synchronisation (see below)
+            copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             dm = device_maps(layout.det, layout.marks, dev, reuse=False)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return dm, ev
 
-    results = []
-    nxt = upload(images[0])
-    for i, img in enumerate(images):
-        dm, ev = nxt
-        nxt = upload(images[i + 1]) if i + 1 < len(images) else None
-        main.wait_event(ev)
-        out = sample_rjmcmc(image_data=img, rng=rng, _device_maps=dm, **params)
+    def collect(out, dm):
         stats = None
+        if callable(out):
+            out = out()  # waits for the chain, reads the configuration back
         if params.get("return_stats"):
             out, stats = out
-        rects = [list(ps) for ps in out]
-        item = rects
+        item = [list(ps) for ps in out]
         if with_scores:
             st = out[-1]._state
             st.use_combinator(params.get("energy_combinator"))
             objs = st.objects()
             rec = np.concatenate([st.proposal_record(u, None) for u in objs]) if objs else None
-            scores = np.exp(st.engine.delta_batch(rec)) if objs else np.zeros(0)
-            item = (rects, scores)
-        if stats is not None:
-            item = (item, stats)
-        results.append(item)
-        del out, dm  # releases the device context and the upload buffers to their pools
+            item = (item, np.exp(st.engine.delta_batch(rec)) if objs else np.zeros(0))
+        return (item, stats) if stats is not None else item
+
+    # three images are in flight: maps of i+1 crossing PCIe, chain i on the SMs, configuration of i-1 being read back and turned
+    # into Rectangles on the host.  Device contexts and upload buffers go back to their pools only after collect(), i.e. after
+    # a host synchronisation that follows their last kernel.
+    defer = (params.get("sampler", "parallel") == "parallel" and params.get("num_samples", 1) == 1 and not with_scores)
+    results, pending = [], None
+    nxt = upload(images[0], first=True)
+    for i, img in enumerate(images):
+        dm, ev = nxt
+        nxt = upload(images[i + 1]) if i + 1 < len(images) else None
+        main.wait_event(ev)
+        out = sample_rjmcmc(image_data=img, rng=rng, _device_maps=dm, _defer=defer, **params)
+        if pending is not None:
+            results.append(collect(*pending))
+        pending = (out, dm)
+        if not defer:
+            results.append(collect(*pending))
+            pending = None
+        del out, dm
+    if pending is not None:
+        results.append(collect(*pending))
     return results
 
 
