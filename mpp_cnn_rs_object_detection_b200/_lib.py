@@ -64,10 +64,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: run `python -m mpp_cnn_rs_object_detection_b200.build` "
+    path = os.environ.get("MPP_B200_LIB", LIB_PATH)  # development: an instrumented build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: run `python -m mpp_cnn_rs_object_detection_b200.build` "
                            f"(the MPP sampler has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, f64, u64 = C.c_void_p, C.c_int, C.c_double, C.c_uint64
     for name in SYMBOLS:
         getattr(lib, name).restype = C.c_int

@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmpp_b200.so")
 SOURCES = ["mpp_b200.cu"]
-HEADERS = ["mpp_device.cuh", "mpp_proposals.cuh", os.path.join("..", "..", "include", "mpp_b200.h")]
+HEADERS = ["mpp_device.cuh", "mpp_clip.cuh", "mpp_proposals.cuh", "mpp_chain.cuh", "mpp_sweep2.cuh", os.path.join("..", "..", "include", "mpp_b200.h")]
 
 
 def _stale() -> bool:

@@ -1311,7 +1311,7 @@ static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj,
     const uint32_t uid_base = h->window_uid_next;
     h->window_uid_next += (uint32_t)(n_wi * n_wj * per_visit);
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;  // wrapped: stay in the upper half
-    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * W2_SCRATCH * sizeof(R);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1365,7 +1365,7 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     const uint32_t uid_base = h->window_uid_next;
     h->window_uid_next += (uint32_t)total * (uint32_t)per_visit;
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;
-    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * (2 * 2 * 9 * 32 + 2 * W2_K) * sizeof(R);
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * W2_SCRATCH * sizeof(R);
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         CUDA_TRY(cudaFuncSetAttribute(k_windows_dataflow<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -16,7 +16,9 @@
 
 #define W2_K 128         // staged objects per window (window +- 64 px)
 #define W2_MAXW 8        // warps per window (speculation depth)
+#define W2_PRE 64        // proposals per visit that can be drawn ahead (= the largest proposals_per_visit)
 #define W2_EPS 1e-16f
+#define W2_SCRATCH (32 + 2 * W2_K)  // per-warp scratch (elements): window row masses of the pre-draw + pair-value stash
 
 enum : unsigned char { W2_ALIVE = 1, W2_WIN = 2, W2_INNER = 4 };
 
@@ -52,6 +54,15 @@ struct WinState {
     short winlist[W2_K];   // SIMT mode: staged indices of the alive window objects
     // speculation results, one slot per warp
     int res_accept[W2_MAXW], res_eval[W2_MAXW];
+    // proposals drawn ahead (warp mode): random words of every proposal of the visit, its kernel under the two mixtures
+    // (index 0: empty window, births only; 1: the reference mixture) and, where that kernel is a birth, the candidate
+    uint32_t pq[8][W2_PRE];
+    unsigned char pkern[2][W2_PRE];
+    int pc_x[2][W2_PRE], pc_y[2][W2_PRE];
+    uint32_t pc_cls[2][W2_PRE];
+    R pc_size[2][W2_PRE], pc_ratio[2][W2_PRE], pc_angle[2][W2_PRE], pc_hl[2][W2_PRE], pc_hw[2][W2_PRE], pc_ca[2][W2_PRE], pc_sa[2][W2_PRE];
+    R pc_pos[2][W2_PRE], pc_dm0[2][W2_PRE], pc_dm1[2][W2_PRE], pc_dm2[2][W2_PRE];
+    float pc_detv[2][W2_PRE], pc_pn0[2][W2_PRE], pc_pn1[2][W2_PRE], pc_pn2[2][W2_PRE];
 };
 
 template <typename R>
@@ -307,18 +318,14 @@ struct Eval {  // outcome of evaluating one proposal (warp-uniform)
 template <typename R, bool DBG>
 __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
                                   float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff) {
-    uint4 q0, q1;
-    philox2(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u, &q0, &q1);
+    // random words and kernel of proposal `it`: drawn ahead by predraw_births (same counter-based stream)
+    const uint4 q0 = make_uint4(w.pq[0][it], w.pq[1][it], w.pq[2][it], w.pq[3][it]);
+    const uint4 q1 = make_uint4(w.pq[4][it], w.pq[5][it], w.pq[6][it], w.pq[7][it]);
     const ModelDev &m = c.m;
     const int nc = w.n_win;
+    const int hyp = nc > 0 ? 1 : 0;
     e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false;
-    // kernel draw
-    int kernel;
-    {
-        const float uk = u01f(q0.x);
-        if (nc > 0) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += w.pkf[k]; if (uk < acc) { kernel = k; break; } } }
-        else kernel = uk < w.pk_e0 ? 0 : 2;
-    }
+    const int kernel = w.pkern[hyp][it];
     e->kernel = kernel;
     const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
     int r = -1;
@@ -332,12 +339,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     bool valid = true;
     float pn[3], dm[3];
     switch (kernel) {
-    case 0: {  // uniform birth in the window
-        a.x = w.x0 + min(wx - 1, (int)(u01f(q0.z) * (float)wx));
-        a.y = w.y0 + min(wy - 1, (int)(u01f(q0.w) * (float)wy));
-        a.size = (R)(u01f(q1.x) * 32.0f); a.ratio = (R)u01f(q1.y); a.angle = (R)(u01f(q1.z) * 3.14159265358979f);
-        a.cls = pack_cls(value_to_class<R>(0, a.size), value_to_class<R>(1, a.ratio), value_to_class<R>(2, a.angle));
-        pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
+    case 0: {  // uniform birth in the window (candidate drawn ahead)
         const float fwd = pk_of(w, 0, nc) / w.lam_unif;
         const float bwd = pk_of(w, 1, nc + 1) / (float)(nc + 1);
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
@@ -350,22 +352,9 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         break;
     }
-    case 2: {  // data-driven birth in the window
+    case 2: {  // data-driven birth in the window (candidate drawn ahead)
         if (!(w.win_mass > 0.0)) { valid = false; break; }
-        const int row = warp_pick_ni(lane < wx ? w.row_mass[lane] : 0.f, u01f(q0.z), lane, nullptr);
-        const float dv = lane < wy ? __ldg(c.det + (size_t)(w.x0 + row) * c.W + w.y0 + lane) : 0.f;
-        const int col = warp_pick_ni(dv, u01f(q0.w), lane, nullptr);
-        a.x = w.x0 + row; a.y = w.y0 + col;
-        const float v0 = __ldg(mark_row(c, 0, a.x, a.y) + lane), v1 = __ldg(mark_row(c, 1, a.x, a.y) + lane), v2 = __ldg(mark_row(c, 2, a.x, a.y) + lane);
-        float s0, s1, s2;
-        const int c0 = warp_pick_ni(v0, u01f(q1.x), lane, &s0), c1 = warp_pick_ni(v1, u01f(q1.y), lane, &s1), c2 = warp_pick_ni(v2, u01f(q1.z), lane, &s2);
-        const float p0 = __shfl_sync(MPP_FULL, v0, c0), p1 = __shfl_sync(MPP_FULL, v1, c1), p2 = __shfl_sync(MPP_FULL, v2, c2);
-        a.cls = pack_cls(c0, c1, c2);
-        a.size = mark_edge<R>(0, c0); a.ratio = mark_edge<R>(1, c1); a.angle = mark_edge<R>(2, c2);
-        a.detv = __shfl_sync(MPP_FULL, dv, col);
-        pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
-        dm[0] = mark_energy_f32(m, 0, p0); dm[1] = mark_energy_f32(m, 1, p1); dm[2] = mark_energy_f32(m, 2, p2);
-        const float fwd = pk_of(w, 2, nc) * dens_of(w, a.detv, pn[0], pn[1], pn[2]) / w.lam_data;
+        const float fwd = pk_of(w, 2, nc) * dens_of(w, w.pc_detv[hyp][it], w.pc_pn0[hyp][it], w.pc_pn1[hyp][it], w.pc_pn2[hyp][it]) / w.lam_data;
         const float bwd = pk_of(w, 3, nc + 1) / (float)(nc + 1);
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
@@ -451,16 +440,24 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     }
     if (!valid) { e->has_add = false; return; }
     if (e->has_add) {
-        a.pos = (R)position_energy_f32(a.detv, m.pos_thr);
-        a.dm0 = (R)dm[0]; a.dm1 = (R)dm[1]; a.dm2 = (R)dm[2];
-        a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
-        const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
-        a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
-        float fs, fc;
-        if (r >= 0 && a.angle == w.angle[r]) {
-            a.ca = w.ca[r]; a.sa = w.sa[r];
+        if (r < 0) {  // birth: everything but the Delta-energy was computed ahead
+            a.x = w.pc_x[hyp][it]; a.y = w.pc_y[hyp][it]; a.cls = w.pc_cls[hyp][it];
+            a.size = w.pc_size[hyp][it]; a.ratio = w.pc_ratio[hyp][it]; a.angle = w.pc_angle[hyp][it];
+            a.hl = w.pc_hl[hyp][it]; a.hw = w.pc_hw[hyp][it]; a.ca = w.pc_ca[hyp][it]; a.sa = w.pc_sa[hyp][it];
+            a.pos = w.pc_pos[hyp][it]; a.dm0 = w.pc_dm0[hyp][it]; a.dm1 = w.pc_dm1[hyp][it]; a.dm2 = w.pc_dm2[hyp][it];
+            a.detv = w.pc_detv[hyp][it]; a.pn0 = w.pc_pn0[hyp][it]; a.pn1 = w.pc_pn1[hyp][it]; a.pn2 = w.pc_pn2[hyp][it];
         } else {
-            __sincosf((float)a.angle, &fs, &fc); a.sa = (R)fs; a.ca = (R)fc;
+            a.pos = (R)position_energy_f32(a.detv, m.pos_thr);
+            a.dm0 = (R)dm[0]; a.dm1 = (R)dm[1]; a.dm2 = (R)dm[2];
+            a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
+            const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
+            a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+            if (a.angle == w.angle[r]) {
+                a.ca = w.ca[r]; a.sa = w.sa[r];
+            } else {
+                float fs, fc;
+                __sincosf((float)a.angle, &fs, &fc); a.sa = (R)fs; a.ca = (R)fc;
+            }
         }
         // capacity of the destination storage cell (MPP_CELL_CAPACITY slots)
         const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
@@ -635,6 +632,86 @@ __device__ __forceinline__ void gather_pixel(const Ctx<R> &c, int x, int y, uint
     *detv = d;
     pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
     dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
+}
+
+// Proposals drawn ahead (warp mode).  A birth (uniform or data-driven) does not depend on the configuration: its position,
+// marks, map values and unit energies are functions of the random words and of the maps only.  One warp therefore draws
+// the births of a whole visit at once, one proposal per lane (every memory round trip is shared by up to 32 proposals),
+// while warp 0 is still staging the neighbourhood; the speculative rounds then only compute Delta-energies.  `hyp`
+// selects the kernel mixture (0: empty window, births only; 1: the reference mixture): both are drawn, the rounds
+// pick the one that matches the window's state at that point of the chain.  `rowm` is 32 floats of warp-private
+// shared memory.  Must be called by a full warp.
+template <typename R>
+__device__ __noinline__ void predraw_births(const Ctx<R> &c, WinState<R> &w, int hyp, int chunk, int per_visit, int x0, int x1, int y0, int y1,
+                                            uint64_t seed, uint32_t win_id, uint64_t sweep_id, R *rowm, int lane) {
+    const ModelDev &m = c.m;
+    const int wx = x1 - x0, wy = y1 - y0;
+    // detection mass of the window rows (same arithmetic as the staging of row_mass / win_mass)
+    double rm = 0.0;
+    {
+        const size_t pitch = (size_t)c.W + 1;
+        if (lane < wx) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
+    }
+    const double win_mass = warp_sum(rm);
+    rowm[lane] = (R)(float)rm;
+    __syncwarp();
+    const int it = chunk * 32 + lane;
+    if (it < per_visit) {
+        Philox rng(seed, win_id, (uint32_t)sweep_id, ((uint32_t)(sweep_id >> 32) << 20) ^ (uint32_t)it ^ 0x77000000u);
+        const uint4 q0 = rng.next(), q1 = rng.next();
+        if (hyp == 0) {
+            w.pq[0][it] = q0.x; w.pq[1][it] = q0.y; w.pq[2][it] = q0.z; w.pq[3][it] = q0.w;
+            w.pq[4][it] = q1.x; w.pq[5][it] = q1.y; w.pq[6][it] = q1.z; w.pq[7][it] = q1.w;
+        }
+        int kernel;
+        {
+            const float uk = u01f(q0.x);
+            if (hyp) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += (float)c.k.p[k]; if (uk < acc) { kernel = k; break; } } }
+            else kernel = uk < (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])) ? 0 : 2;
+        }
+        w.pkern[hyp][it] = (unsigned char)kernel;
+        int x = 0, y = 0;
+        uint32_t cls = 0;
+        R size = 0, ratio = 0, angle = 0;
+        bool birth = false;
+        if (kernel == 0) {  // uniform birth in the window
+            x = x0 + min(wx - 1, (int)(u01f(q0.z) * (float)wx));
+            y = y0 + min(wy - 1, (int)(u01f(q0.w) * (float)wy));
+            size = (R)(u01f(q1.x) * 32.0f); ratio = (R)u01f(q1.y); angle = (R)(u01f(q1.z) * 3.14159265358979f);
+            cls = pack_cls(value_to_class<R>(0, size), value_to_class<R>(1, ratio), value_to_class<R>(2, angle));
+            birth = true;
+        } else if (kernel == 2 && win_mass > 0.0) {  // data-driven birth: pixel ~ detection map, marks ~ mark maps at the pixel
+            float acc = 0.f;
+            const float tr = u01f(q0.z) * (float)win_mass;
+            int row = 0;
+            for (int k = 0; k < wx; ++k) { const float v = (float)rowm[k]; if (v > 0.f) { row = k; acc += v; if (acc > tr) break; } }
+            float dv;
+            const int col = scan_pick_global(c.det + (size_t)(x0 + row) * c.W + y0, wy, u01f(q0.w) * (float)rowm[row], &dv);
+            x = x0 + row; y = y0 + col;
+            const size_t pix = (size_t)x * c.W + y, plane = (size_t)c.H * c.W;
+            float pv;
+            const int c0 = scan_pick_row(mark_row(c, 0, x, y), u01f(q1.x) * __ldg(c.marksum + pix), &pv);
+            const int c1 = scan_pick_row(mark_row(c, 1, x, y), u01f(q1.y) * __ldg(c.marksum + plane + pix), &pv);
+            const int c2 = scan_pick_row(mark_row(c, 2, x, y), u01f(q1.z) * __ldg(c.marksum + 2 * plane + pix), &pv);
+            cls = pack_cls(c0, c1, c2);
+            size = mark_edge<R>(0, c0); ratio = mark_edge<R>(1, c1); angle = mark_edge<R>(2, c2);
+            birth = true;
+        }
+        if (birth) {
+            float detv, pn[3], dm[3];
+            gather_pixel(c, x, y, cls, &detv, pn, dm);
+            const R length = ((R)2 * size) / ((R)1 + ratio);
+            float fs, fc;
+            __sincosf((float)angle, &fs, &fc);
+            w.pc_x[hyp][it] = x; w.pc_y[hyp][it] = y; w.pc_cls[hyp][it] = cls;
+            w.pc_size[hyp][it] = size; w.pc_ratio[hyp][it] = ratio; w.pc_angle[hyp][it] = angle;
+            w.pc_hl[hyp][it] = length / (R)2; w.pc_hw[hyp][it] = ratio * length / (R)2; w.pc_ca[hyp][it] = (R)fc; w.pc_sa[hyp][it] = (R)fs;
+            w.pc_pos[hyp][it] = (R)position_energy_f32(detv, m.pos_thr);
+            w.pc_dm0[hyp][it] = (R)dm[0]; w.pc_dm1[hyp][it] = (R)dm[1]; w.pc_dm2[hyp][it] = (R)dm[2];
+            w.pc_detv[hyp][it] = detv; w.pc_pn0[hyp][it] = pn[0]; w.pc_pn1[hyp][it] = pn[1]; w.pc_pn2[hyp][it] = pn[2];
+        }
+    }
+    __syncwarp();
 }
 
 // Delta-energy of removing staged entry r and/or adding `a`, computed by ONE thread over the staged state
@@ -937,6 +1014,74 @@ __device__ __forceinline__ void rebuild_winlist(WinState<R> &w, int lane) {
 
 template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(MPP_FULL, v, src); }
 
+// Empty window (warp mode): every proposal is a birth whose candidate was drawn ahead, so the visit only has Delta-energies
+// and accept tests left.  A warp evaluates 32 / G births at once, G lanes per birth (the staged objects are spread over the
+// G lanes, reductions by width-G shuffles): with 8 warps and G = 8 the 32 proposals of a visit take ONE pass, and a visit
+// that accepts nothing (the common case in an empty window) ends there.  Called by full warps; `it` is uniform within a
+// group of G lanes (it < 0: idle group).  Returns the accept decision; *evaluated as in evaluate_proposal.
+template <typename R, bool DBG>
+__device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinState<R> &w, int it, int G, float temp, int lane, R *sx, R *sy, Cand<R> *out,
+                                                  bool *evaluated, int *kernel_out, float *dbg_maxdiff) {
+    const ModelDev &m = c.m;
+    const int j = lane & (G - 1);
+    bool live = it >= 0;
+    int kernel = 0;
+    Cand<R> &a = *out;
+    if (live) {
+        kernel = w.pkern[0][it];
+        if (kernel == 2 && !(w.win_mass > 0.0)) live = false;
+    }
+    if (live) {
+        a.x = w.pc_x[0][it]; a.y = w.pc_y[0][it]; a.cls = w.pc_cls[0][it];
+        a.size = w.pc_size[0][it]; a.ratio = w.pc_ratio[0][it]; a.angle = w.pc_angle[0][it];
+        a.hl = w.pc_hl[0][it]; a.hw = w.pc_hw[0][it]; a.ca = w.pc_ca[0][it]; a.sa = w.pc_sa[0][it];
+        a.pos = w.pc_pos[0][it]; a.dm0 = w.pc_dm0[0][it]; a.dm1 = w.pc_dm1[0][it]; a.dm2 = w.pc_dm2[0][it];
+        a.detv = w.pc_detv[0][it]; a.pn0 = w.pc_pn0[0][it]; a.pn1 = w.pc_pn1[0][it]; a.pn2 = w.pc_pn2[0][it];
+        if (w.cmask[((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0)] == 0xffffffffu) live = false;  // destination storage cell full
+    }
+    *kernel_out = kernel;
+    // Delta-energy: the objects whose reductions the new object changes, spread over the lanes of the group
+    R acc = 0, ov_add = 0, al_add = 0;
+    if (live) {
+        Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
+        const R rad_a = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+        const int n = w.n;
+        for (int k = j; k < n; k += G) {
+            if (!(w.flags[k] & W2_ALIVE)) continue;
+            const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
+            if (d2 > m.max_d2) continue;
+            R ov_a = w.ov1[k], al_a = w.al1[k];
+            if (d2 <= m.ov_d2) { const R o = pair_ov_w(m, w, k, ga, rad_a, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
+            if (d2 <= m.al_d2) { const R al = align_magnitude(geo_w(w, k), ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
+            acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, w.ov1[k], w.al1[k]);
+        }
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        acc += __shfl_xor_sync(MPP_FULL, acc, off);
+        ov_add = r_max(ov_add, __shfl_xor_sync(MPP_FULL, ov_add, off));
+        al_add = r_max(al_add, __shfl_xor_sync(MPP_FULL, al_add, off));
+    }
+    *evaluated = live;
+    if (!live) return false;
+    Terms<R> t;
+    t.pos = a.pos;
+    shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
+    t.ov = ov_add; t.al = (m.rewarding ? (R)-1 : (R)1) * al_add;
+    t.area = area_prior_fast<R>(m, a.hl, a.hw);
+    t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
+    const R de = acc + combine_fast(m, t);
+#ifndef MPP_TRACE
+    if (DBG && dbg_maxdiff && j == 0) {
+        const float diff = fabsf((float)(de - delta_lane_brute(m, w, -1, true, a, sx, sy)));
+        atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
+    }
+#endif
+    const float fwd = kernel == 0 ? pk_of(w, 0, 0) / w.lam_unif : pk_of(w, 2, 0) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2) / w.lam_data;
+    const float bwd = pk_of(w, kernel + 1, 1);  // / (nc + 1) = 1
+    const float log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
+    return __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / temp + log_ratio;
+}
+
 // the speculative rounds of one visit in SIMT mode (one warp)
 template <typename R, bool DBG>
 __device__ __forceinline__ void simt_rounds(const Ctx<R> &c, WinState<R> &w, int per_visit, float temp, uint64_t seed, uint32_t win_id, uint64_t sweep_id,
@@ -986,9 +1131,9 @@ template <typename R, int NW, bool DBG, bool SIMT = false>
 __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi, int wj, int ox, int oy, int per_visit, float temp,
                              uint64_t seed, uint64_t sweep_id, uint32_t uid_first, float *dbg_maxdiff) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int PER_WARP = 2 * 2 * 9 * 32 + 2 * W2_K;  // clip ping-pong buffers + pair-value stash
-    R *sx = scratch + (size_t)warp * PER_WARP + lane, *sy = sx + 2 * 9 * 32;
-    R *po = scratch + (size_t)warp * PER_WARP + 2 * 2 * 9 * 32, *pa = po + W2_K;
+    constexpr int PER_WARP = W2_SCRATCH;
+    R *sx = scratch + (size_t)warp * PER_WARP, *sy = sx;  // (unused by the register-only clip; kept in the signatures)
+    R *po = scratch + (size_t)warp * PER_WARP + 32, *pa = po + W2_K;
     const uint32_t win_id = (uint32_t)wi * 65536u + (uint32_t)wj;
     const ModelDev &m = c.m;
     const int px0 = 32 * wi - ox, py0 = 32 * wj - oy;
@@ -1064,6 +1209,14 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
         if (lane == 0) { w.n = n; w.n_win = 0; }
     }
+    if (!SIMT) {  // meanwhile the other warps draw the births of the visit ahead (NW == 1: warp 0, afterwards)
+        constexpr int PW0 = NW > 1 ? 1 : 0, NPW = NW > 1 ? NW - 1 : 1;
+        if (warp >= PW0) {
+            const int n_jobs = 2 * ((per_visit + 31) >> 5);
+            for (int job = warp - PW0; job < n_jobs; job += NPW)
+                predraw_births(c, w, job & 1, job >> 1, per_visit, x0, x1, y0, y1, seed, win_id, sweep_id, scratch + (size_t)warp * PER_WARP, lane);
+        }
+    }
     __syncthreads();
     MPP_MARK(1);
     const int n0 = w.n;
@@ -1113,6 +1266,57 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 
     // ------------------------------------------------------------------ speculative proposal rounds
     int it = 0;
+    if (!SIMT && w.n_win == 0) {  // empty window: births only, 32 / G of them per warp at once (see evaluate_birth_group)
+#ifdef MPP_TRACE
+        const long long t_p = clock64();
+#endif
+        const int L0 = (per_visit + NW - 1) / NW;                          // proposals per warp
+        const int L = L0 <= 1 ? 1 : (L0 <= 2 ? 2 : (L0 <= 4 ? 4 : (L0 <= 8 ? 8 : (L0 <= 16 ? 16 : 32))));
+        const int G = 32 / L, P = min(per_visit, L * NW);
+        const int mine = warp * L + lane / G;
+        Cand<R> a;
+        bool ev = false;
+        int kern = 0;
+        const bool acc = evaluate_birth_group<R, DBG>(c, w, mine < P ? mine : -1, G, temp, lane, sx, sy, &a, &ev, &kern, dbg_maxdiff);
+        __syncwarp();
+        const bool head = (lane & (G - 1)) == 0;
+        const uint32_t bal = __ballot_sync(MPP_FULL, acc && head), evb = __ballot_sync(MPP_FULL, ev && head);
+        if (lane == 0) { w.res_accept[warp] = bal ? warp * L + (__ffs(bal) - 1) / G : 0x7fffffff; w.res_eval[warp] = (int)evb; }
+        __syncthreads();
+        int first = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) first = min(first, w.res_accept[q]);
+        const int used = first == 0x7fffffff ? P : first + 1;
+        if (warp == 0 && lane == 0) {
+            int evn = 0;
+            for (int q = 0; q < NW; ++q) {
+                const int cnt = min(max(used - q * L, 0), L) * G;  // lanes of warp q whose proposals were consumed
+                evn += __popc((uint32_t)w.res_eval[q] & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
+            }
+            w.n_eval += evn; w.n_done += used;
+        }
+        if (first != 0x7fffffff && warp == first / L) {
+            const int src = (first % L) * G;
+            Eval<R> g;  // the accepted birth, broadcast from the first lane of its group
+            g.kernel = bcast(kern, src); g.r = -1; g.has_add = true; g.evaluated = true; g.accept = true;
+            g.a.x = bcast(a.x, src); g.a.y = bcast(a.y, src); g.a.cls = bcast(a.cls, src);
+            g.a.size = bcast(a.size, src); g.a.ratio = bcast(a.ratio, src); g.a.angle = bcast(a.angle, src);
+            g.a.hl = bcast(a.hl, src); g.a.hw = bcast(a.hw, src); g.a.ca = bcast(a.ca, src); g.a.sa = bcast(a.sa, src);
+            g.a.pos = bcast(a.pos, src); g.a.dm0 = bcast(a.dm0, src); g.a.dm1 = bcast(a.dm1, src); g.a.dm2 = bcast(a.dm2, src);
+            g.a.detv = bcast(a.detv, src); g.a.pn0 = bcast(a.pn0, src); g.a.pn1 = bcast(a.pn1, src); g.a.pn2 = bcast(a.pn2, src);
+            if (lane == 0) { w.n_acc += 1; w.n_birth += 1; }
+            if (w.n >= W2_K) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
+            else {
+                fill_pairs(m, w, -1, true, g.a, lane, sx, sy, po, pa);
+                commit_proposal(c, w, g, first, lane, sx, sy, po, pa);
+            }
+        }
+        __syncthreads();
+        it = used;
+#ifdef MPP_TRACE
+        t_eval += clock64() - t_p;
+#endif
+    }
     if (SIMT) {  // lane-per-proposal mode: the CTA is one warp
 #ifdef MPP_TRACE
         const long long t_s = clock64();

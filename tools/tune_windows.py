@@ -18,6 +18,8 @@ spec = ModelSpec(setup="legacy", pos_threshold=C["detection_threshold"], remap_c
 configs = ((1, 32, "dataflow"), (2, 32, "dataflow"), (4, 32, "dataflow"), (8, 32, "dataflow"), (2, 16, "dataflow"), (4, 16, "dataflow")) if size > 2048 else \
     ((4, 16, "colours"), (4, 32, "colours"), (1, 16, "dataflow"), (2, 16, "dataflow"), (4, 16, "dataflow"), (4, 32, "dataflow"), (8, 16, "dataflow"),
      (8, 32, "dataflow"), (8, 64, "dataflow"), (2, 32, "dataflow"))
+if os.environ.get("MPP_TUNE"):
+    configs = tuple((int(a.split(':')[0]), int(a.split(':')[1]), "dataflow") for a in os.environ["MPP_TUNE"].split(','))
 for nw, pv, sched in configs:
     eng = Engine((size, size), device=dev)
     eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
