@@ -1480,7 +1480,8 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
                 __nanosleep(100);
             }
         }
-        __syncthreads();
+        // no barrier here: the other warps start drawing the visit's births ahead (they only read the maps) while warp 0
+        // is still waiting; window_visit's first barrier comes after warp 0 has staged the neighbourhood
         window_visit<R, NW, DBG, SIMT>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
                                  uid_base + (uint32_t)t * (uint32_t)per_visit, dbg_maxdiff);
         __syncthreads();

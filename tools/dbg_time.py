@@ -12,7 +12,7 @@ Cc, H = bench.CALIB_HRCM, bench.HRC
 spec = ModelSpec(setup="legacy", pos_threshold=Cc["detection_threshold"], remap_coefs=Cc["coefs"], remap_intercepts=Cc["intercepts"],
                  min_area=Cc["min_area"], max_area=Cc["max_area"], combinator="hierarchical",
                  comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
-for nw, pv in ((8, 32),):
+for nw, pv in ((8, 64),):
     eng = Engine((size, size), device=dev)
     eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
     eng.add_objects(objs[:, :2], objs[:, 2:5])
