@@ -94,18 +94,24 @@ __device__ __forceinline__ float mark_energy_f32(const ModelDev &m, int i, float
     return 1.0f - __fdividef(2.0f, 1.0f + __expf(-z));
 }
 
-// det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): one coalesced
-// 128-byte row per mark (lane = class) + one 4-byte gather, all independent -> a single memory round trip.
+// det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): seven independent gathers
 template <typename R>
-__device__ __noinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
-    const float v0 = __ldg(mark_row(c, 0, x, y) + lane), v1 = __ldg(mark_row(c, 1, x, y) + lane), v2 = __ldg(mark_row(c, 2, x, y) + lane);
-    const float d = __ldg(c.det + (size_t)x * c.W + y);
-    const float s0 = warp_sum(v0), s1 = warp_sum(v1), s2 = warp_sum(v2);
-    const float p0 = __shfl_sync(MPP_FULL, v0, cls_of(cls, 0)), p1 = __shfl_sync(MPP_FULL, v1, cls_of(cls, 1)),
-                p2 = __shfl_sync(MPP_FULL, v2, cls_of(cls, 2));
+__device__ __forceinline__ void gather_pixel(const Ctx<R> &c, int x, int y, uint32_t cls, float *detv, float *pn, float *dm) {
+    const size_t pix = (size_t)x * c.W + y, plane = (size_t)c.H * c.W;
+    const float d = __ldg(c.det + pix);
+    const float p0 = __ldg(mark_row(c, 0, x, y) + cls_of(cls, 0)), p1 = __ldg(mark_row(c, 1, x, y) + cls_of(cls, 1)),
+                p2 = __ldg(mark_row(c, 2, x, y) + cls_of(cls, 2));
+    const float s0 = __ldg(c.marksum + pix), s1 = __ldg(c.marksum + plane + pix), s2 = __ldg(c.marksum + 2 * plane + pix);
     *detv = d;
     pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
     dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
+}
+
+// out-of-line copy for the warp-uniform callers of the rounds (every lane issues the same seven gathers: one transaction each)
+template <typename R>
+__device__ __noinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
+    (void)lane;
+    gather_pixel(c, x, y, cls, detv, pn, dm);
 }
 
 template <typename R>
@@ -619,19 +625,6 @@ __device__ __forceinline__ int scan_pick_row(const float *row, float target, flo
 #pragma unroll
     for (int k = 0; k < 8; ++k) { const float4 q = __ldg(r4 + k); v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
     return scan32(v, 32, target, picked);
-}
-
-// det value, per-mark energies and normalised mark probabilities of classes `cls` at pixel (x, y): seven independent gathers
-template <typename R>
-__device__ __forceinline__ void gather_pixel(const Ctx<R> &c, int x, int y, uint32_t cls, float *detv, float *pn, float *dm) {
-    const size_t pix = (size_t)x * c.W + y, plane = (size_t)c.H * c.W;
-    const float d = __ldg(c.det + pix);
-    const float p0 = __ldg(mark_row(c, 0, x, y) + cls_of(cls, 0)), p1 = __ldg(mark_row(c, 1, x, y) + cls_of(cls, 1)),
-                p2 = __ldg(mark_row(c, 2, x, y) + cls_of(cls, 2));
-    const float s0 = __ldg(c.marksum + pix), s1 = __ldg(c.marksum + plane + pix), s2 = __ldg(c.marksum + 2 * plane + pix);
-    *detv = d;
-    pn[0] = __fdividef(p0, s0); pn[1] = __fdividef(p1, s1); pn[2] = __fdividef(p2, s2);
-    dm[0] = mark_energy_f32(c.m, 0, p0); dm[1] = mark_energy_f32(c.m, 1, p1); dm[2] = mark_energy_f32(c.m, 2, p2);
 }
 
 // Proposals drawn ahead (warp mode).  A birth (uniform or data-driven) does not depend on the configuration: its position,
@@ -1248,19 +1241,17 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     }
     __syncthreads();
     MPP_MARK(3);
-    // phase D: per-mark details of the window objects (deaths, translations, mark transforms), one warp per object;
-    // phase E: partner reductions of everything a move in the window can affect, one thread per object
-    for (int k = warp; k < n0; k += NW) {
-        if (!(w.flags[k] & W2_WIN)) continue;
-        float detv, pn[3], dm[3];
-        pixel_info(c, w.x[k], w.y[k], w.cls[k], lane, &detv, pn, dm);
-        if (lane == 0) {
+    // phase D: per-mark details of the window objects (deaths, translations, mark transforms): seven gathers per object;
+    // phase E: partner reductions of everything a move in the window can affect; one thread per object for both
+    for (int k = threadIdx.x; k < n0; k += 32 * NW) {
+        if (w.flags[k] & W2_WIN) {
+            float detv, pn[3], dm[3];
+            gather_pixel(c, w.x[k], w.y[k], w.cls[k], &detv, pn, dm);
             w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
             w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
         }
-    }
-    for (int k = threadIdx.x; k < n0; k += 32 * NW)
         if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, true, true, sx, sy);
+    }
     __syncthreads();
     MPP_MARK(4);
 
