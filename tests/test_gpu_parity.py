@@ -163,3 +163,45 @@ def test_error_conventions():
         eng.remove_objects(h)  # KeyError in the reference (energy_point_set.py:88-100)
     assert e.value.code == ERR_NOT_FOUND
     assert len(eng) == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_pair_overlap_structured_cases_match_oracle(precision):
+    """mpp_pair_values (PairEnergy.compute, base_energies.py:77-80) on rectangle pairs that stress the intersection routine:
+    identical, nested, collinear edges, touching from outside, touching at a corner, perpendicular, class-aligned angles,
+    extreme size ratios -- against the oracle's polygon clip (RectangleOverlapEnergy, prior_energies.py:12-24)."""
+    from oracle import mpp_oracle as orc
+    from tests.gpu_util import make_engine
+    h = w = 704
+    det = np.full((h, w), 0.5, dtype=np.float32)
+    marks = [np.full((h, w, 32), 1.0 / 32, dtype=np.float32) for _ in range(3)]
+    eng = make_engine("nocalib", det, marks, precision)
+    rng = np.random.default_rng(5)
+    pi = np.pi
+    # (dx, dy, sizeA, ratioA, angleA, sizeB, ratioB, angleB)
+    cases = [(0, 0, 6, 0.5, 0.0, 6, 0.5, 0.0), (0, 4, 6, 0.5, 0.0, 6, 0.5, 0.0), (0, 8, 6, 0.5, 0.0, 6, 0.5, 0.0), (4, 8, 6, 0.5, 0.0, 6, 0.5, 0.0),
+             (0, 1, 12, 0.75, 0.0, 3, 0.5, 0.0), (1, 0, 3, 0.5, 0.3, 12, 0.75, 0.3), (0, 0, 6, 0.5, 0.0, 6, 0.5, pi / 2), (2, 1, 8, 1.0, 0.0, 8, 1.0, pi / 4),
+             (1, 1, 6, 0.5, 0.3, 6, 0.5, 0.3), (3, 2, 6, 0.5, 5 * pi / 32, 6, 0.5, 5 * pi / 32), (3, 2, 6, 0.5, 5 * pi / 32, 6, 0.5, 21 * pi / 32),
+             (2, 2, 30, 0.2, 1.0, 1.0, 0.9, 2.0), (5, 5, 31, 1.0, 0.1, 0.7, 0.3, 0.2), (9, 0, 6, 0.5, 0.0, 6, 0.5, 0.0), (0, 0, 20, 1.0, 0.0, 20, 1.0, pi / 4)]
+    for _ in range(200):
+        cases.append((int(rng.integers(-12, 13)), int(rng.integers(-12, 13)), float(rng.uniform(1, 31)), float(rng.uniform(0.1, 1)),
+                      float(rng.integers(0, 32) * pi / 32 if rng.random() < 0.5 else rng.uniform(0, pi)),
+                      float(rng.uniform(1, 31)), float(rng.uniform(0.1, 1)), float(rng.integers(0, 32) * pi / 32 if rng.random() < 0.5 else rng.uniform(0, pi))))
+    xy, mk = [], []
+    for i, (dx, dy, sa, ra, aa, sb, rb, ab) in enumerate(cases):  # one pair per 40-px block
+        cx, cy = 40 + 40 * (i % ((w - 80) // 40)), 40 + 40 * (i // ((w - 80) // 40))
+        assert cx + 32 < h and cy + 32 < w, "scene too small for the structured cases"
+        xy += [(cx, cy), (cx + dx, cy + dy)]
+        mk += [(sa, ra, aa), (sb, rb, ab)]
+    handles = eng.add_objects(np.array(xy), np.array(mk))
+    got = eng.pair_values(handles[0::2], handles[1::2])[:, 0]
+    want = np.array([orc.OracleScene.overlap_energy(orc.ORect(*xy[2 * i], *mk[2 * i]), orc.ORect(*xy[2 * i + 1], *mk[2 * i + 1]))
+                     if (xy[2 * i][0] - xy[2 * i + 1][0]) ** 2 + (xy[2 * i][1] - xy[2 * i + 1][1]) ** 2 <= 32 ** 2 else 0.0 for i in range(len(cases))])
+    if precision == "fp32":
+        # float32 geometry: absolute error of the intersection area ~1e-5 px^2 x coordinates; the ratio to a sub-pixel
+        # rectangle's area (cases 12, 13) amplifies it, hence the looser relative bound there
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
+        big = np.array([min(c[2], c[5]) >= 3 for c in cases])
+        np.testing.assert_allclose(got[big], want[big], rtol=1e-5, atol=1e-5)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)

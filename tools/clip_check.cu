@@ -1,5 +1,6 @@
 // Host check of mpp_clip::quad_box_area against a float64 Sutherland-Hodgman clip (development tool):
-//   nvcc -O2 -o /tmp/clip_check tools/clip_check.cu && /tmp/clip_check
+//   g++ -O2 -x c++ -o /tmp/clip_check tools/clip_check.cu && /tmp/clip_check [percent of the full case count]
+// (plain C++: mpp_clip.cuh compiles without nvcc; tests/test_clip_cpu.py runs a reduced count)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +51,8 @@ static void quad_of(double dx, double dy, double angA, double angB, double hlB, 
 
 static double urand() { return (double)rand() / ((double)RAND_MAX + 1.0); }
 
-int main() {
+int main(int argc, char **argv) {
+    const long scale = argc > 1 ? atol(argv[1]) : 100;  // percent of the full case count
     srand(1234);
     double worst_f = 0, worst_d = 0, worst_sh = 0;
     long n_cases = 0, n_pos = 0;
@@ -88,7 +90,7 @@ int main() {
     run(0, 0, 0, PI / 4, 4, 4, 2.9, 2.9, true);   // small diamond, corners poke out? (2.9*sqrt2 = 4.1)
     run(5, 5, 0.2, 1.1, 5, 2.5, 6, 1, true);
     // random: continuous angles
-    for (int i = 0; i < 2000000; ++i) {
+    for (long i = 0; i < 20000 * scale; ++i) {
         const double sA = 1 + 31 * urand(), rA = 0.1 + 0.9 * urand(), sB = 1 + 31 * urand(), rB = 0.1 + 0.9 * urand();
         const double lA = 2 * sA / (1 + rA), lB = 2 * sB / (1 + rB);
         const bool classes = (i & 1);
@@ -97,7 +99,7 @@ int main() {
         run(rand() % (2 * rng + 1) - rng, rand() % (2 * rng + 1) - rng, angA, angB, lA / 2, rA * lA / 2, lB / 2, rB * lB / 2, false);
     }
     // near-degenerate: almost parallel, almost touching
-    for (int i = 0; i < 500000; ++i) {
+    for (long i = 0; i < 5000 * scale; ++i) {
         const double h = 2 + 6 * urand(), w = 1 + 3 * urand();
         const double eps = std::pow(10.0, -2 - 6 * urand()) * (urand() < 0.5 ? -1 : 1);
         const double ang = PI * urand();
