@@ -421,3 +421,51 @@ def test_plugin_combinators_mlp_and_manual():
             after = eps.apply_perturbation(p)
             e1 = after.energy_graph.compute_subset(list(after), energy_combinator=comb)
             assert abs((e1 - e0) - d) < 2e-4 + 1e-5 * abs(e0), (type(comb).__name__, k, e1 - e0, d)
+
+
+def test_training_helpers_energy_vectors_and_kernel_walks():
+    """energy_utils.compute_many_energy_vectors (energy_utils.py:69-82) on the reference's perturbed configurations against the
+    reference's own vectors (tests/golden/training_helpers.npz), and the kernel walks of perturbation_sampler.py:127-169."""
+    api = _api()
+    g = gu.load("training_helpers.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, "legacy")
+    image = _image(api, det, marks)
+    image.gt_config = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    ue, pe = setup.make_energies(image)
+    cfgs = []
+    for name in ("light", "overlap", "strong"):
+        flat, lens = g[f"pert_{name}"], g[f"pert_{name}_len"]
+        off = 0
+        for n in lens:
+            cfgs.append([api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in flat[off:off + n]])
+            off += n
+    names = [str(s) for s in g["energy_names"]]
+    assert names == setup.energy_names
+    vec = api.compute_many_energy_vectors(cfgs, image, ue, pe, names)
+    assert vec.shape == g["vectors"].shape
+
+    def canon(m):  # the reference lists a configuration's objects in set-iteration order: compare as multisets of rows
+        return m[np.lexsort(np.round(m, 4).T[::-1])]
+    off = 0
+    for c in cfgs:
+        np.testing.assert_allclose(canon(vec[off:off + len(c)]), canon(g["vectors"][off:off + len(c)]), rtol=1e-5, atol=1e-5)
+        off += len(c)
+    one, got_names = api.compute_energy_vector(cfgs[0], ue, pe, det.shape, names, return_names=True)
+    np.testing.assert_allclose(canon(one), canon(g["vectors"][:len(cfgs[0])]), rtol=1e-5, atol=1e-5)
+    assert set(got_names) == set(names) and api.names_from_energies(ue + pe) == [e.name for e in ue + pe]
+    assert api.compute_many_energy_vectors([], image, ue, pe, names).shape == (0, len(names))
+    # kernel walks: iter_per_point * n moves from the ground truth; the aggregated perturbation turns the start into the end
+    rng = np.random.default_rng(4)
+    walks = api.sample_multiple_kernel_perturbations(image, n_samples=2, rng=rng, energy_setup=setup, iter_per_point=0.5)
+    assert len(walks) == 2 and all(isinstance(w, api.EPointsSet) for w in walks)
+    perts = api.sample_multiple_kernel_perturbations(image, n_samples=1, rng=rng, energy_setup=setup, iter_per_point=0.5,
+                                                     return_perturbations=True, aggregate_pert=True)
+    agg = perts[0]
+    start = api.EPointsSet(image.gt_config, det.shape, ue, pe)
+    kernels, p_kernels = api.make_kernels(image, intensity=1.0, rng=rng)
+    end, seq = api.sample_kernel_perturbations(kernels, p_kernels, 0.5, start, rng)
+    assert len(seq) == int(0.5 * len(start)) and len(start) == len(image.gt_config)
+    net = api.aggregate_perturbations(seq)
+    want = (set(start) - set(net.removal)) | set(net.addition)
+    assert set(end) == want and isinstance(agg.removal, list) and isinstance(agg.addition, list)
