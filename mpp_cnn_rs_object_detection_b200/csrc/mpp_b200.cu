@@ -139,6 +139,8 @@ __global__ void k_mark_sums(const float *__restrict__ marks, size_t n_rows, floa
 }
 
 // single-block inclusive scan of doubles in place (ncell <= a few 1e5)
+__global__ void k_inv_total(double *cdf, int n) { cdf[n] = cdf[n - 1] > 0.0 ? 1.0 / cdf[n - 1] : 0.0; }
+
 __global__ void k_scan_double(double *v, int n) {
     __shared__ double part[1024];
     const int t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
@@ -868,7 +870,7 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     const size_t rec = precision == MPP_PRECISION_FP64 ? sizeof(Rec<double>) : sizeof(Rec<float>);
     CUDA_TRY(cudaMalloc(&h->d_mask, sizeof(uint32_t) * h->ncell));
     CUDA_TRY(cudaMalloc(&h->d_recs, rec * (size_t)h->ncell * MPP_CELL_CAPACITY));
-    CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * h->ncell));
+    CUDA_TRY(cudaMalloc(&h->d_cell_cdf, sizeof(double) * (h->ncell + 1)));  // [ncell]: 1 / total mass
     CUDA_TRY(cudaMalloc(&h->d_rowcum, sizeof(double) * (size_t)height * ((size_t)width + 1)));
     CUDA_TRY(cudaMalloc(&h->d_marksum, sizeof(float) * 3 * (size_t)height * (size_t)width));
     CUDA_TRY(cudaMalloc(&h->d_scan, sizeof(int) * (h->ncell + 1)));
@@ -938,6 +940,7 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
     const int blocks = (h->ncell + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     k_cell_mass<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->ny, h->ncell, h->d_cell_cdf);
     k_scan_double<<<1, 1024, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
+    k_inv_total<<<1, 1, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
     k_row_prefix<<<(h->H + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->d_rowcum);
     {
         const size_t n_rows = (size_t)3 * h->H * h->W, n_warps = (n_rows + 31) / 32;
@@ -1037,7 +1040,9 @@ int mpp_set_kernels(mpp_ctx *h, const mpp_kernel_params *p) {
     if (!(p->intensity > 0.0)) return fail(MPP_ERR_INVALID, "mpp_set_kernels: intensity must be > 0");
     if (p->data_translation_max_delta < 0 || p->data_translation_max_delta > 15) return fail(MPP_ERR_INVALID, "mpp_set_kernels: max_delta in [0,15]");
     KernDev &k = h->k;
-    for (int i = 0; i < 8; ++i) k.p[i] = p->p_kernel[i];
+    for (int i = 0; i < 8; ++i) { k.p[i] = p->p_kernel[i]; k.pf[i] = (float)p->p_kernel[i]; }
+    k.pk_e0 = (float)(k.p[0] / (k.p[0] + k.p[2])); k.pk_e2 = (float)(k.p[2] / (k.p[0] + k.p[2]));
+    k.unif_scale = p->intensity / ((double)h->H * (double)h->W);
     k.intensity = p->intensity;
     k.trl_sigma = p->gauss_translation_sigma;
     k.trl_max_delta = p->data_translation_max_delta;

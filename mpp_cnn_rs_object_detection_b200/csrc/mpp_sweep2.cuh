@@ -659,8 +659,8 @@ __device__ __noinline__ void predraw_births(const Ctx<R> &c, WinState<R> &w, int
         int kernel;
         {
             const float uk = u01f(q0.x);
-            if (hyp) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += (float)c.k.p[k]; if (uk < acc) { kernel = k; break; } } }
-            else kernel = uk < (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])) ? 0 : 2;
+            if (hyp) { float acc = 0; kernel = 7; for (int k = 0; k < 7; ++k) { acc += c.k.pf[k]; if (uk < acc) { kernel = k; break; } } }
+            else kernel = uk < c.k.pk_e0 ? 0 : 2;
         }
         w.pkern[hyp][it] = (unsigned char)kernel;
         int x = 0, y = 0;
@@ -1157,10 +1157,10 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
                 w.ccell[q] = ok ? cy + cx * c.ny : -1;
                 w.cmask[q] = ok ? __ldcg(c.mask + cy + cx * c.ny) : 0xffffffffu;
             }
-            for (int k = 0; k < 8; ++k) w.pkf[k] = (float)c.k.p[k];
-            w.pk_e0 = (float)(c.k.p[0] / (c.k.p[0] + c.k.p[2])); w.pk_e2 = (float)(c.k.p[2] / (c.k.p[0] + c.k.p[2]));
+            for (int k = 0; k < 8; ++k) w.pkf[k] = c.k.pf[k];
+            w.pk_e0 = c.k.pk_e0; w.pk_e2 = c.k.pk_e2;
             w.dens_scale = (float)c.H * (float)c.W * 32768.0f / c.det_sum;
-            w.lam_unif = (float)(c.k.intensity * ((double)(x1 - x0) * (double)(y1 - y0)) / ((double)c.H * (double)c.W));
+            w.lam_unif = (float)(c.k.unif_scale * (double)((x1 - x0) * (y1 - y0)));
         }
         {   // detection mass of the window rows
             const size_t pitch = (size_t)c.W + 1;
@@ -1168,7 +1168,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             if (lane < x1 - x0) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
             w.row_mass[lane] = (float)rm;
             const double tot = warp_sum(rm);
-            if (lane == 0) { w.win_mass = tot; w.lam_data = (float)(c.k.intensity * tot / c.cell_cdf[c.ncell - 1]); }
+            if (lane == 0) { w.win_mass = tot; w.lam_data = (float)(c.k.intensity * tot * c.cell_cdf[c.ncell]); }  // [ncell] = 1 / total mass
         }
         const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
         const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
