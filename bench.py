@@ -305,7 +305,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from mpp_cnn_rs_object_detection_b200 import synth
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg, synth
     from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec, kernel_probabilities
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -315,6 +315,9 @@ def run_b200(args):
         raise RuntimeError("bench.py (product arm) needs a CUDA device: the MPP sampler has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # one process per GPU: keep each rank (and the pinned host buffers it allocates) on its GPU's NUMA node, so that the
+    # uploads of all ranks do not cross the socket interconnect (single-GPU runs keep every core for the CPU baseline leg)
+    numa_cpus = mg.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -430,6 +433,7 @@ def run_b200(args):
         e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4),
                "d2h_bytes_per_step": int(tot["objects"] * (4 + 8 + 24 + 4)), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
                "objects_found": tot["objects"], "gpu_launches": int(tot["launches"]),
+               "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
                "call": "api.sample_rjmcmc_batch([ImageWMaps with pinned host maps] x steps, init_config='naive', fixed T) -> List[Rectangle] per image",
                "timer": "host wall clock around the call; whole batch incl. pipeline fill; per image: H2D of its maps (overlapped with the "
                         "previous image's sampling) + prefix sums + naive init + sampler + D2H of the configuration (overlapped with the next image's sampling); max over ranks"}

@@ -25,6 +25,32 @@ BAND_ALIGN = 32    # band boundaries are multiples of the cell size
 RECORD = 8         # doubles per packed object (mpp_pack_rows)
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pins the calling process (and therefore the pinned host buffers it allocates afterwards: first touch) to the CPUs of the
+    NUMA node the GPU hangs off, so that with one process per GPU the host-to-device uploads of all ranks do not cross the
+    socket interconnect.  Returns the CPU list, or None when the topology is not exposed (then nothing is changed)."""
+    import os
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus += list(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.append(int(part))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except (OSError, AttributeError, ValueError):
+        return None
+
+
 def shard_items(n_items: int, world: int, rank: int) -> List[int]:
     """Round-robin assignment of independent tiles / images to ranks."""
     return list(range(rank, n_items, world))
