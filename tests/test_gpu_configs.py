@@ -101,6 +101,17 @@ def test_edge_cases():
                                     init_config="naive", init_temperature=0.02, alpha_t=1.0, burn_in=3000, energy_setup=setup,
                                     samples_interval=100, target_temperature=0.0)
     assert len(batch) == 2 and len(batch[0][1]) == len(batch[0][0][0]) and np.all(batch[0][1] > 0)
+    # the pipelined batch (upload / chain / read-back of consecutive images overlapped) returns what one call per image returns
+    kw = dict(num_samples=1, energy_combinator=comb, init_config="naive", init_temperature=0.02, alpha_t=1.0, burn_in=3000, energy_setup=setup,
+              samples_interval=100, target_temperature=0.0)
+    imgs = [img, api.ImageWMaps("f", det.shape, None, det.copy(), [m.copy() for m in marks], api.default_mappings(), ["size", "ratio", "angle"]), img]
+    piped = api.sample_rjmcmc_batch(imgs, np.random.default_rng(7), return_stats=True, **kw)
+    rng1 = np.random.default_rng(7)
+    for (rects, stats), im in zip(piped, imgs):
+        one = api.sample_rjmcmc(im, rng1, **kw)
+        key = lambda r: (r.x, r.y, r.size, r.ratio, r.angle)
+        assert sorted(map(key, rects[-1])) == sorted(map(key, one[-1]))
+        assert stats["proposals"] > 3000 and stats["evaluated"] <= stats["proposals"] and stats["launches"] >= 1
     # capacity errors are reported, not silently ignored: 33 objects in one 32x32 cell
     from mpp_cnn_rs_object_detection_b200._lib import ERR_CELL_FULL, MPPError
     eng = make_engine("legacy", det, marks, "fp32")
