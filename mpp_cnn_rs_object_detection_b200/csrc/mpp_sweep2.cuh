@@ -1118,6 +1118,10 @@ __device__ __forceinline__ void simt_rounds(const Ctx<R> &c, WinState<R> &w, int
     }
 }
 
+// barrier among the `n_threads` (a multiple of 32) threads of the warps that stage a visit (named barrier 1; barrier 0 is
+// __syncthreads)
+__device__ __forceinline__ void stage_sync(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
 // One visit of window (wi, wj) of the grid shifted by (ox, oy): staging, `per_visit` proposals, publication.
 // `uid_first` is the uid of the first object this visit may create.  Must be called by the whole CTA.
 template <typename R, int NW, bool DBG, bool SIMT = false>
@@ -1142,6 +1146,17 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 #endif
 
     // ------------------------------------------------------------------ staging
+    // Two groups of warps work side by side until the barrier in front of the rounds: warps 1..npre draw the births of the
+    // visit ahead (they only read the maps), warp 0 and the remaining warps stage the neighbourhood (phases A-E, synchronised
+    // among themselves by named barrier 1).
+    const int n_jobs = 2 * ((per_visit + 31) >> 5);                         // (kernel mixture, chunk of 32 proposals)
+    const int npre = (SIMT || NW == 1) ? 0 : min(n_jobs, NW - 1);
+    const bool stager = warp == 0 || warp > npre;
+    const int sg = 32 * (NW - npre), sidx = warp == 0 ? lane : (warp - npre) * 32 + lane;
+    if (!stager) {
+        for (int job = warp - 1; job < n_jobs; job += npre)
+            predraw_births(c, w, job & 1, job >> 1, per_visit, x0, x1, y0, y1, seed, win_id, sweep_id, scratch + (size_t)warp * PER_WARP, lane);
+    } else {
     // phase A (warp 0): window constants; handles / position keys of the objects within 64 px of the window
     if (warp == 0) {
         if (lane == 0) {
@@ -1202,19 +1217,14 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
         if (lane == 0) { w.n = n; w.n_win = 0; }
     }
-    if (!SIMT) {  // meanwhile the other warps draw the births of the visit ahead (NW == 1: warp 0, afterwards)
-        constexpr int PW0 = NW > 1 ? 1 : 0, NPW = NW > 1 ? NW - 1 : 1;
-        if (warp >= PW0) {
-            const int n_jobs = 2 * ((per_visit + 31) >> 5);
-            for (int job = warp - PW0; job < n_jobs; job += NPW)
-                predraw_births(c, w, job & 1, job >> 1, per_visit, x0, x1, y0, y1, seed, win_id, sweep_id, scratch + (size_t)warp * PER_WARP, lane);
-        }
-    }
-    __syncthreads();
+    if (!SIMT && NW == 1)  // a single warp does everything, one after the other
+        for (int job = 0; job < n_jobs; ++job)
+            predraw_births(c, w, job & 1, job >> 1, per_visit, x0, x1, y0, y1, seed, win_id, sweep_id, scratch, lane);
+    stage_sync(sg);
     MPP_MARK(1);
     const int n0 = w.n;
     // phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
-    for (int k = threadIdx.x; k < n0; k += 32 * NW) {
+    for (int k = sidx; k < n0; k += sg) {
         const int key = w.x[k];
         const uint32_t u = w.uid[k];
         int rank = 0;
@@ -1224,10 +1234,10 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
         w.order[rank] = w.handle[k];
     }
-    __syncthreads();
+    stage_sync(sg);
     MPP_MARK(2);
     // phase C: one thread per object loads its full record
-    for (int p = threadIdx.x; p < n0; p += 32 * NW) {
+    for (int p = sidx; p < n0; p += sg) {
         const uint32_t h = w.order[p];
         const Rec<R> rec = load_rec(c.recs + h);
         const bool inw = rec.x >= x0 && rec.x < x1 && rec.y >= y0 && rec.y < y1;
@@ -1239,11 +1249,11 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
         if (inw) atomicAdd(&w.n_win, 1);
     }
-    __syncthreads();
+    stage_sync(sg);
     MPP_MARK(3);
     // phase D: per-mark details of the window objects (deaths, translations, mark transforms): seven gathers per object;
     // phase E: partner reductions of everything a move in the window can affect; one thread per object for both
-    for (int k = threadIdx.x; k < n0; k += 32 * NW) {
+    for (int k = sidx; k < n0; k += sg) {
         if (w.flags[k] & W2_WIN) {
             float detv, pn[3], dm[3];
             gather_pixel(c, w.x[k], w.y[k], w.cls[k], &detv, pn, dm);
@@ -1252,6 +1262,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
         if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, true, true, sx, sy);
     }
+    }  // stager
     __syncthreads();
     MPP_MARK(4);
 
