@@ -317,6 +317,7 @@ template <typename R>
 struct Eval {  // outcome of evaluating one proposal (warp-uniform)
     int kernel, r;
     bool has_add, evaluated, accept;
+    bool noop;  // accepted proposal that maps the configuration onto itself (see evaluate_proposal): nothing to commit
     Cand<R> a;
 };
 
@@ -330,7 +331,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     const ModelDev &m = c.m;
     const int nc = w.n_win;
     const int hyp = nc > 0 ? 1 : 0;
-    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false;
+    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false; e->noop = false;
     const int kernel = w.pkern[hyp][it];
     e->kernel = kernel;
     const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
@@ -379,6 +380,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         const int nx_ = min(max((int)((float)w.x[r] + d0 * (float)c.k.trl_sigma), 0), c.H - 1);
         const int ny_ = min(max((int)((float)w.y[r] + d1 * (float)c.k.trl_sigma), 0), c.W - 1);
         if (nx_ < w.x0 || nx_ >= w.x1 || ny_ < w.y0 || ny_ >= w.y1) { valid = false; break; }
+        if (nx_ == w.x[r] && ny_ == w.y[r]) { e->noop = true; break; }  // the shift rounds to zero
         a.x = nx_; a.y = ny_; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
         e->has_add = true;
@@ -397,6 +399,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         const int col = warp_pick_ni(dv, u01f(q0.w), lane, nullptr);
         const int ex = X0 + row, ey = Y0 + col;
         if (ex < w.x0 || ex >= w.x1 || ey < w.y0 || ey >= w.y1) { valid = false; break; }
+        if (ex == w.x[r] && ey == w.y[r]) { e->noop = true; break; }  // the object's own pixel was drawn
         a.x = ex; a.y = ey; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
         // backward window (around the end point) + the maps at the end point, one round trip
         const int BX0 = max(0, ex - md), BX1 = min(ex + md + 1, c.H), BY0 = max(0, ey - md), BY1 = min(ey + md + 1, c.W);
@@ -428,6 +431,8 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         } else {
             ncls = warp_pick_ni(v, u01f(q0.w), lane, &s);
             nv = mark_edge<R>(pid, ncls);
+            // the object's own class was drawn and its mark already sits on that class's value: same object
+            if (ncls == ocls && nv == (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r]))) { e->noop = true; break; }
             const float pf = __shfl_sync(MPP_FULL, v, ncls) / s, pb = __shfl_sync(MPP_FULL, v, ocls) / s;
             log_ratio = __logf(pb + W2_EPS) - __logf(pf + W2_EPS);  // p_kernel / n cancel
         }
@@ -445,6 +450,13 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     }
     }
     if (!valid) { e->has_add = false; return; }
+    if (e->noop) {
+        // The proposal maps the configuration onto itself: Delta-energy 0 and equal forward / backward densities, so the Green
+        // ratio is 1 and the reference accepts it (replacing the object by an equal one).  It counts as evaluated and accepted,
+        // but there is nothing to commit, and later proposals evaluated against the same state in this round stay valid.
+        e->has_add = false; e->evaluated = true; e->accept = true;
+        return;
+    }
     if (e->has_add) {
         if (r < 0) {  // birth: everything but the Delta-energy was computed ahead
             a.x = w.pc_x[hyp][it]; a.y = w.pc_y[hyp][it]; a.cls = w.pc_cls[hyp][it];
@@ -1337,20 +1349,25 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const long long t_a = clock64();
 #endif
         if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff);
-        else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; }
-        if (lane == 0) { w.res_accept[warp] = e.accept ? 1 : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
+        else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.noop = false; }
+        if (lane == 0) { w.res_accept[warp] = e.accept ? (e.noop ? 2 : 1) : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
         __syncthreads();
 #ifdef MPP_TRACE
         const long long t_b = clock64();
 #endif
         int first = NW;
 #pragma unroll
-        for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q]) first = q;
+        for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q] == 1) first = q;  // first accepted proposal that changes the state
         const int used = min(first + 1, min(NW, per_visit - it));  // proposals of the chain consumed by this round
-        if (warp == 0 && lane == 0) { int ev = 0; for (int q = 0; q < used; ++q) ev += w.res_eval[q]; w.n_eval += ev; w.n_done += used; }
+        if (warp == 0 && lane == 0) {
+            int ev = 0, same = 0;
+            for (int q = 0; q < used; ++q) { ev += w.res_eval[q]; same += w.res_accept[q] == 2; }
+            w.n_eval += ev; w.n_done += used;
+            if (same) atomicAdd(&w.n_acc, same);  // the committing warp updates the same counter
+        }
         if (first < NW && warp == first) {
             if (lane == 0) {
-                w.n_acc += 1;
+                atomicAdd(&w.n_acc, 1);
                 if (e.has_add && e.r < 0) w.n_birth += 1;
                 if (!e.has_add && e.r >= 0) w.n_death += 1;
             }
