@@ -1026,7 +1026,7 @@ template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return 
 // group of G lanes (it < 0: idle group).  Returns the accept decision; *evaluated as in evaluate_proposal.
 template <typename R, bool DBG>
 __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinState<R> &w, int it, int G, float temp, int lane, R *sx, R *sy, Cand<R> *out,
-                                                  bool *evaluated, int *kernel_out, float *dbg_maxdiff) {
+                                                  bool *evaluated, int *kernel_out, const int *near, int n_near, float *dbg_maxdiff) {
     const ModelDev &m = c.m;
     const int j = lane & (G - 1);
     bool live = it >= 0;
@@ -1050,9 +1050,8 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
     if (live) {
         Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
         const R rad_a = r_sqrt(a.hl * a.hl + a.hw * a.hw);
-        const int n = w.n;
-        for (int k = j; k < n; k += G) {
-            if (!(w.flags[k] & W2_ALIVE)) continue;
+        for (int i = j; i < n_near; i += G) {  // `near`: the alive staged objects within reach of the window (W2_INNER), ascending
+            const int k = near[i];
             const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
             if (d2 > m.max_d2) continue;
             R ov_a = w.ov1[k], al_a = w.al1[k];
@@ -1288,10 +1287,22 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const int L = L0 <= 1 ? 1 : (L0 <= 2 ? 2 : (L0 <= 4 ? 4 : (L0 <= 8 ? 8 : (L0 <= 16 ? 16 : 32))));
         const int G = 32 / L, P = min(per_visit, L * NW);
         const int mine = warp * L + lane / G;
+        // only the staged objects within 32 px of the window can interact with a birth inside it: compact their indices
+        // (per warp, in the pair-value stash, which is free until a commit)
+        int *near = reinterpret_cast<int *>(po);
+        int n_near = 0;
+        for (int b = 0; b < w.n; b += 32) {
+            const int k = b + lane;
+            const bool in = k < w.n && (w.flags[k] & (W2_ALIVE | W2_INNER)) == (W2_ALIVE | W2_INNER);
+            const uint32_t bal = __ballot_sync(MPP_FULL, in);
+            if (in) near[n_near + __popc(bal & ((1u << lane) - 1))] = k;
+            n_near += __popc(bal);
+        }
+        __syncwarp();
         Cand<R> a;
         bool ev = false;
         int kern = 0;
-        const bool acc = evaluate_birth_group<R, DBG>(c, w, mine < P ? mine : -1, G, temp, lane, sx, sy, &a, &ev, &kern, dbg_maxdiff);
+        const bool acc = evaluate_birth_group<R, DBG>(c, w, mine < P ? mine : -1, G, temp, lane, sx, sy, &a, &ev, &kern, near, n_near, dbg_maxdiff);
         __syncwarp();
         const bool head = (lane & (G - 1)) == 0;
         const uint32_t bal = __ballot_sync(MPP_FULL, acc && head), evb = __ballot_sync(MPP_FULL, ev && head);
