@@ -59,8 +59,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--n-rect", type=int, default=0, help="candidate rectangles (0: 2600 per 2048^2, scaled by area)")
-    ap.add_argument("--sweeps", type=int, default=9)
-    ap.add_argument("--per-visit", type=int, default=64)
+    ap.add_argument("--sweeps", type=int, default=6)
+    ap.add_argument("--per-visit", type=int, default=96)
     ap.add_argument("--warps", type=int, default=8, help="warps per window (speculation depth) of the window sampler")
     ap.add_argument("--sampler", default="windows", choices=["windows", "cells"],
                     help="windows: mpp_run_windows (production); cells: mpp_run_sweeps (first-generation aligned cells)")

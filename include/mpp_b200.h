@@ -235,7 +235,7 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
 
 /* Parallel sampler, second generation (the production path).  Sampling windows are the 32-px grid cells shifted by a
  * per-sweep pseudo-random offset, coloured 3x3; one CTA per window stages everything within 64 px of its window in
- * shared memory once and runs `proposals_per_visit` (<= 64) proposals from there; its `n_warps` (1, 2, 4, 8) warps
+ * shared memory once and runs `proposals_per_visit` (<= 128) proposals from there; its `n_warps` (1, 2, 4, 8) warps
  * evaluate consecutive proposals speculatively (the chain does not depend on n_warps).  The kernel mixture is the
  * reference's when a window holds objects and births-only when it is empty.  debug_maxdiff (device float, may be
  * NULL): every Delta-energy is also recomputed by brute force and the largest |difference| is written there.

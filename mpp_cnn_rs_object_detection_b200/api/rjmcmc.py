@@ -201,7 +201,7 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                   init_config: Union[str, List[Rectangle], None], init_temperature: float, alpha_t: Union[float, str], burn_in: int,
                   energy_setup: EnergySetup, samples_interval: int, target_temperature: float, verbose: int = 0,
                   iter_multiplier: float = None, use_split_merge: bool = False, sampler: str = "parallel",
-                  proposals_per_visit: int = 64, warps_per_window: int = 8, precision: str = "fp32",
+                  proposals_per_visit: int = 96, warps_per_window: int = 8, precision: str = "fp32",
                   reuse_device_maps: bool = True, return_stats: bool = False, _device_maps=None, _defer: bool = False):
     """Drop-in for sample_rjmcmc (sample_rjmcmc.py:38-102): returns a list of `num_samples` PointsSet of Rectangle.
 
@@ -389,7 +389,7 @@ def sample_rjmcmc_tiles(images, rng: np.random.Generator, n_streams: int = 8, **
         burn_in, interval, alpha_t = burn_in * mult, interval * mult, np.power(alpha_t, 1 / mult)
     if isinstance(alpha_t, str) and alpha_t == "auto":
         alpha_t, t_target = np.power(t_target / t0, 1 / burn_in), 0
-    pv, nw = int(params.get("proposals_per_visit", 64)), int(params.get("warps_per_window", 8))
+    pv, nw = int(params.get("proposals_per_visit", 96)), int(params.get("warps_per_window", 8))
     max_iter = int(burn_in) + 2 * int(interval)
     dev = torch.device("cuda", torch.cuda.current_device())
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(n_streams, len(images))))]

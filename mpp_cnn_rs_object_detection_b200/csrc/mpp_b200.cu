@@ -40,6 +40,7 @@ struct mpp_ctx {
     bool maps_set = false, model_set = false, kernels_set = false;
     ModelDev m;
     KernDev k;
+    float visit_alpha = 1.f, visit_tfloor = 0.f;  // temperature decay inside a window visit (set per mpp_run_windows call)
     int *h_pinned = nullptr;            // small pinned read-back area (16 x 8 bytes)
     void *d_plan = nullptr;             // device scratch of the dataflow schedule (offsets, temperatures, completion grids)
     size_t plan_bytes = 0;
@@ -69,6 +70,7 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.marksum = h->d_marksum;
     c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
     c.m = h->m; c.k = h->k;
+    c.visit_alpha = h->visit_alpha; c.visit_tfloor = h->visit_tfloor;
     return c;
 }
 
@@ -1393,13 +1395,18 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
 extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_warps, int schedule, double t0, double alpha_t, double t_target,
                                uint64_t seed, uint64_t sweep_offset, unsigned long long *counters_host, float *debug_maxdiff) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_windows: set maps, model and kernels first");
-    if (n_sweeps < 0 || per_visit < 1 || per_visit > 64 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 64)");
+    if (n_sweeps < 0 || per_visit < 1 || per_visit > W2_PRE || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows: bad arguments (1 <= proposals_per_visit <= 128)");
     if (n_warps != 0 && n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8)
         return fail(MPP_ERR_INVALID, "mpp_run_windows: n_warps must be 0 (lane-per-proposal mode), 1, 2, 4 or 8");
     if (schedule != 0 && schedule != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows: schedule must be 0 (colour barriers) or 1 (dataflow)");
     if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
     if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_windows: the window sampler is float32 only (use mpp_run_chain / mpp_replay for float64)");
     CUDA_TRY(cudaSetDevice(h->device));
+    // `alpha_t` is the temperature factor of one sweep; inside a visit the i-th proposal of every window stands for step
+    // i * (number of windows) of the sweep, so the temperature decays by alpha_t^(1/per_visit) per proposal index and the
+    // schedule is the reference's geometric one (rjmcmc.py:158-159) whatever the number of proposals per visit
+    h->visit_alpha = (alpha_t > 0.0 && alpha_t < 1.0) ? (float)pow(alpha_t, 1.0 / (double)per_visit) : 1.f;
+    h->visit_tfloor = (float)t_target;
     if (schedule == 1 && n_sweeps > 0) {
         int rc;
 #define MPP_LAUNCH_D(NWV) (debug_maxdiff \
@@ -1454,11 +1461,12 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
 extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, double temperature, uint64_t seed, uint64_t sweep_id, int ci,
                                    int row_lo, int row_hi) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_window_rows: set maps, model and kernels first");
-    if (per_visit < 1 || per_visit > 64 || !(temperature > 0.0) || ci < 0 || ci > 2 || row_lo > row_hi)
+    if (per_visit < 1 || per_visit > W2_PRE || !(temperature > 0.0) || ci < 0 || ci > 2 || row_lo > row_hi)
         return fail(MPP_ERR_INVALID, "mpp_run_window_rows: bad arguments");
     if (n_warps != 0 && n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: n_warps must be 0, 1, 2, 4 or 8");
     if (h->m.setup == MPP_SETUP_TOY || h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_window_rows: float32 map-driven model only");
     CUDA_TRY(cudaSetDevice(h->device));
+    h->visit_alpha = 1.f; h->visit_tfloor = 0.f;  // one temperature per phase
     const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
     const int ox = (int)(hsh & 31), oy = (int)((hsh >> 5) & 31);
     const int nwx = (h->H + ox + 31) / 32, nwy = (h->W + oy + 31) / 32;

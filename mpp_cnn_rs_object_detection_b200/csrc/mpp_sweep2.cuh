@@ -16,7 +16,7 @@
 
 #define W2_K 128         // staged objects per window (window +- 64 px)
 #define W2_MAXW 8        // warps per window (speculation depth)
-#define W2_PRE 64        // proposals per visit that can be drawn ahead (= the largest proposals_per_visit)
+#define W2_PRE 128       // proposals per visit that can be drawn ahead (= the largest proposals_per_visit)
 #define W2_EPS 1e-16f
 #define W2_SCRATCH (32 + 2 * W2_K)  // per-warp scratch (elements): window row masses of the pre-draw + pair-value stash
 
@@ -313,6 +313,14 @@ __device__ __forceinline__ int pick_window_object(const WinState<R> &w, int j, i
     return -1;
 }
 
+// temperature of proposal `it` of a visit that starts at `temp` (see mpp_run_windows): geometric decay per proposal index,
+// stopping at the target temperature like the reference's `if T > T_target: T *= alpha`
+template <typename R>
+__device__ __forceinline__ float visit_temp(const Ctx<R> &c, float temp, int it) {
+    if (c.visit_alpha == 1.f) return temp;
+    return fmaxf(temp * __powf(c.visit_alpha, (float)it), fminf(temp, c.visit_tfloor));
+}
+
 template <typename R>
 struct Eval {  // outcome of evaluating one proposal (warp-uniform)
     int kernel, r;
@@ -491,7 +499,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (lane == 0) atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
     }
 #endif
-    const float la = -(float)de / temp + log_ratio;
+    const float la = -(float)de / visit_temp(c, temp, it) + log_ratio;
     e->evaluated = true;
     e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
 
@@ -977,7 +985,7 @@ __device__ __forceinline__ void evaluate_lane(const Ctx<R> &c, const WinState<R>
         const float diff = fabsf((float)(de - delta_lane_brute(m, w, r, has_add, a, sx, sy)));
         atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
     }
-    const float la = -(float)de / temp + log_ratio;
+    const float la = -(float)de / visit_temp(c, temp, it) + log_ratio;
     e->evaluated = true;
     e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
 }
@@ -1083,7 +1091,7 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
     const float fwd = kernel == 0 ? pk_of(w, 0, 0) / w.lam_unif : pk_of(w, 2, 0) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2) / w.lam_data;
     const float bwd = pk_of(w, kernel + 1, 1);  // / (nc + 1) = 1
     const float log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
-    return __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / temp + log_ratio;
+    return __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / visit_temp(c, temp, it) + log_ratio;
 }
 
 // the speculative rounds of one visit in SIMT mode (one warp)

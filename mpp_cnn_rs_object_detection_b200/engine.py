@@ -357,7 +357,7 @@ class Engine:
         self.launches += int(n_sweeps) * stride * stride
         return [int(v) for v in cnt] if read_counters else None
 
-    def run_windows(self, n_sweeps: int, proposals_per_visit: int = 64, n_warps: int = 8, t0: float = 1.0, alpha_t: float = 1.0,
+    def run_windows(self, n_sweeps: int, proposals_per_visit: int = 96, n_warps: int = 8, t0: float = 1.0, alpha_t: float = 1.0,
                     t_target: float = 0.0, seed: int = 0, sweep_offset: int = 0, read_counters: bool = True, debug: bool = False,
                     schedule: str = "dataflow"):
         """Production parallel sampler (mpp_run_windows): shifted 32-px windows, shared-memory resident visits, speculative

@@ -11,7 +11,7 @@ for pid in (2781, 2789, 2794):
         img, objs = _val_image(api, pid)
     except KeyError:
         continue
-    for pv in (16, 32, 64):
+    for pv in (64, 96, 128):
         rs, ps, ns = [], [], []
         for seed in range(4):
             model = api.MPPModel(cfg, model_dir=os.path.join(GOLD, "model_mpp_hrcM"))
