@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 
 # DRAM bytes (read + write) per evaluated proposal of k_windows_dataflow<float,8>, from the ncu --set full capture
 # profiles/r01_prof_dataflow_raw.csv: (259.9168 + 34.889984) MB for 531 615 evaluated proposals in the launch
-NCU_DRAM_BYTES_PER_PROPOSAL = 838.8
+NCU_DRAM_BYTES_PER_PROPOSAL = 738.1
 METRIC = "rjmcmc_proposals_per_sec"
 UNIT = "proposals/s"
 
