@@ -24,7 +24,7 @@ for n_streams in (8, 32):
             e.add_objects(objs[:, :2], objs[:, 2:5])
             engines.append(e)
     torch.cuda.synchronize()
-    sweeps, pv, nw = 20, 64, NW
+    sweeps, pv, nw = 12, 96, NW
     for rep in range(2):
         t = time.perf_counter()
         for i, e in enumerate(engines):
