@@ -237,8 +237,13 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
  * per-sweep pseudo-random offset, coloured 3x3; one CTA per window stages everything within 64 px of its window in
  * shared memory once and runs `proposals_per_visit` (<= 128) proposals from there; its `n_warps` (1, 2, 4, 8) warps
  * evaluate consecutive proposals speculatively (the chain does not depend on n_warps).  The kernel mixture is the
- * reference's when a window holds objects and births-only when it is empty.  debug_maxdiff (device float, may be
- * NULL): every Delta-energy is also recomputed by brute force and the largest |difference| is written there.
+ * reference's when a window holds objects and births-only when it is empty.  n_warps = 0 selects the (slower)
+ * lane-per-proposal mode.  `alpha_t` is the temperature factor of one SWEEP (the reference's per-step factor,
+ * rjmcmc.py:158-159, to the power of the proposals of a sweep); inside a visit the temperature decays by
+ * alpha_t^(1/proposals_per_visit) per proposal index, so the schedule as a function of the number of proposals made is
+ * the reference's for any proposals_per_visit; it stops at t_target.  A proposal that maps the configuration onto itself
+ * (own class / own pixel drawn) is accepted, as in the reference, without touching the state.  debug_maxdiff (device
+ * float, may be NULL): every Delta-energy is also recomputed by brute force and the largest |difference| is written there.
  * schedule 0: one launch per colour class (9 per sweep, a device-wide barrier between colours).  schedule 1: one
  * persistent kernel for the whole call; window visits are claimed in (sweep, colour, window) order and each starts as soon
  * as the earlier visits within 64 px of it have completed (dataflow; same chain as schedule 0, bit for bit).
@@ -252,7 +257,7 @@ int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_w
  * apart, so ranks that own disjoint row bands of one scene can run this concurrently and only need to exchange their
  * boundary objects (mpp_pack_rows / mpp_unpack_rows) between two values of ci.  The grid offset, the random streams and
  * the uids of born objects depend only on (seed, sweep_id, window): a split scene follows the same chain as
- * mpp_run_windows(schedule 0) on one GPU.  mpp_window_grid returns the grid offset of a sweep. */
+ * mpp_run_windows(schedule 0) on one GPU (one temperature per call).  mpp_window_grid returns the grid offset of a sweep. */
 int mpp_run_window_rows(mpp_ctx *ctx, int proposals_per_visit, int n_warps, double temperature, uint64_t seed,
                         uint64_t sweep_id, int ci, int row_lo, int row_hi);
 int mpp_window_grid(mpp_ctx *ctx, uint64_t seed, uint64_t sweep_id, int *ox_host, int *oy_host);
