@@ -145,3 +145,12 @@ def test_split_scene_follows_the_single_gpu_chain(world):
     np.testing.assert_array_equal(xy1[o1], xy2[o2])
     np.testing.assert_array_equal(mk1[o1], mk2[o2])
     assert abs(len(xy1) - len(objs)) < len(objs)  # the chain did something sensible
+
+
+def test_soak_speculation_depths_annealing_and_brute_force_check():
+    """tools/soak.py: five scenes (sparse to dense, T from 0.02 to 1, with and without annealing inside the visit), 7 to 128
+    proposals per visit: the chain, the counters and the uids are the same for 1, 4 and 8 speculating warps, the counters are
+    consistent with the object count, and every Delta-energy agrees with its brute-force recomputation."""
+    import os
+    import runpy
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "soak.py"), run_name="__main__")
