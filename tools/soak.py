@@ -21,7 +21,7 @@ for seed, size, n_rect, temp, alpha in ((1, 256, 60, 0.02, 1.0), (2, 256, 160, 0
         for nw in (1, 4, 8):
             eng = Engine((size, size + 37), device=dev)
             eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
-            eng.add_objects(objs[:, :2], objs[:, 2:5])
+            eng.add_objects(objs[:, :2], objs[:, 2:5], uid=np.arange(len(objs)))  # explicit uids: the device would number them in arrival order
             cnt, maxdiff = eng.run_windows(6, pv, nw, t0=temp, alpha_t=alpha, t_target=0.001, seed=seed * 11, debug=True)
             worst = max(worst, maxdiff)
             _, xy, mk, uid = eng.read_objects()
