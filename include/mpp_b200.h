@@ -132,7 +132,8 @@ typedef struct {
 /* ---------------------------------------------------------------------------------------------- library */
 int mpp_abi_version(void);
 const char *mpp_last_error(void);
-/* sizeof of the ABI structs as compiled: 0 mpp_model_params, 1 mpp_kernel_params, 2 mpp_proposal, 3 mpp_step_result */
+/* sizeof of the ABI structs as compiled: 0 mpp_model_params, 1 mpp_kernel_params, 2 mpp_proposal, 3 mpp_step_result,
+ * 4 mpp_window_trace */
 int mpp_abi_struct_size(int which);
 
 /* ---------------------------------------------------------------------------------------------- context
@@ -251,6 +252,41 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
 int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, int schedule, double t0,
                     double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
                     unsigned long long *counters_host, float *debug_maxdiff);
+
+/* Per-proposal trace of the window sampler: what RJMCMC.step (rjmcmc.py:83-164) computes for one step -- the kernel
+ * drawn (:88), the perturbation (:90), the Delta-energy (:93-100), the proposal densities (:102-103), the temperature and
+ * the accept test (:105-113) -- written by the debug instantiation of the production kernels (mpp_run_windows with
+ * debug_maxdiff != NULL) so that a CPU oracle can re-derive every Green ratio from first principles.  One 64-byte record
+ * per proposal of the chain; a proposal that was evaluated speculatively and discarded is overwritten when it is re-drawn,
+ * so the buffer ends up holding exactly the chain.  Record of proposal `it` of the visit of window (wi, wj) in sweep s:
+ *   index = (s - sweep0) * (nx + 2) * (ny + 2) * proposals_per_visit + (wi * (ny + 2) + wj) * proposals_per_visit + it
+ * with nx = ceil(H / 32), ny = ceil(W / 32).  Records past `capacity` are dropped. */
+#define MPP_TRACE_WRITTEN 1u      /* the proposal was drawn */
+#define MPP_TRACE_EVALUATED 2u    /* its Delta-energy was evaluated (otherwise: rejected before, see the REASON bits) */
+#define MPP_TRACE_ACCEPT 4u
+#define MPP_TRACE_IDENTITY 8u     /* the proposal maps the configuration onto itself (accepted, nothing committed) */
+#define MPP_TRACE_HAS_ADD 16u
+#define MPP_TRACE_HAS_REM 32u
+#define MPP_TRACE_LEFT_WINDOW 64u /* a move whose end point lies outside the window (or a data-driven kernel over zero mass) */
+#define MPP_TRACE_CELL_FULL 128u  /* destination storage cell has no free slot */
+typedef struct {
+    uint32_t flags;          /* MPP_TRACE_* | kernel << 8 | min(n_window_objects, 255) << 16 | param_id << 24 */
+    uint32_t rem_uid;        /* uid of the removed object (HAS_REM) */
+    uint32_t add_uid;        /* uid the added object gets if accepted (HAS_ADD) */
+    uint32_t add_cls;        /* packed classes of the added object: size | ratio << 8 | angle << 16 */
+    int32_t add_x, add_y;
+    float add_size, add_ratio, add_angle;
+    float delta_e;           /* Delta-energy as the kernel computed it (top-2 partner reductions, float32) */
+    float log_ratio;         /* log(backward density) - log(forward density) */
+    float temperature;
+    float u_accept;          /* the accept uniform: accepted iff log(u + 1e-16) < -delta_e / temperature + log_ratio */
+    uint32_t q[3];           /* random words: kernel choice, object choice, accept (Philox4x32-10 keyed by seed, counter
+                                (0|1, wi * 65536 + wj, sweep, it ^ 0x77000000)) */
+} mpp_window_trace;
+
+/* Arms (buf != NULL) or disarms the trace of the next mpp_run_windows(debug_maxdiff != NULL) calls on this context.
+ * buf: device memory for `capacity` records, zero-filled by the caller; sweep0: sweep id of the first traced sweep. */
+int mpp_set_window_trace(mpp_ctx *ctx, mpp_window_trace *buf, uint64_t capacity, uint64_t sweep0);
 
 /* One third of a sweep of the window sampler, restricted to a band of rows: the three colour launches (cj = 0, 1, 2) of
  * the window rows wi = ci (mod 3) whose first pixel row lies in [row_lo, row_hi).  Window rows of equal ci are >= 65 px

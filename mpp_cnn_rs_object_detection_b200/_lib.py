@@ -42,13 +42,22 @@ PROPOSAL_DTYPE = np.dtype([("kernel", "<i4"), ("rem_x", "<i4"), ("rem_y", "<i4")
 STEP_RESULT_DTYPE = np.dtype([("delta_e", "<f8"), ("fwd", "<f8"), ("bwd", "<f8"), ("log_alpha", "<f8"),
                               ("temperature", "<f8"), ("accepted", "<i4"), ("n_after", "<i4")], align=True)
 
+# mpp_window_trace: one record per proposal of the window sampler (debug instantiation)
+WINDOW_TRACE_DTYPE = np.dtype([("flags", "<u4"), ("rem_uid", "<u4"), ("add_uid", "<u4"), ("add_cls", "<u4"), ("add_x", "<i4"),
+                               ("add_y", "<i4"), ("add_size", "<f4"), ("add_ratio", "<f4"), ("add_angle", "<f4"),
+                               ("delta_e", "<f4"), ("log_ratio", "<f4"), ("temperature", "<f4"), ("u_accept", "<f4"),
+                               ("q", "<u4", (3,))], align=True)
+TRACE_WRITTEN, TRACE_EVALUATED, TRACE_ACCEPT, TRACE_IDENTITY, TRACE_HAS_ADD, TRACE_HAS_REM, TRACE_LEFT_WINDOW, TRACE_CELL_FULL = \
+    1, 2, 4, 8, 16, 32, 64, 128
+
 # every symbol include/mpp_b200.h declares
 SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_create", "mpp_ctx_destroy", "mpp_set_maps",
            "mpp_set_model", "mpp_set_kernels", "mpp_add_objects", "mpp_remove_objects", "mpp_clear_objects",
            "mpp_num_objects", "mpp_read_objects", "mpp_energy_vectors", "mpp_delta_batch", "mpp_replay",
            "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
-           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid"]
+           "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid",
+           "mpp_set_window_trace"]
 
 _lib = None
 
@@ -64,7 +73,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("MPP_B200_LIB", LIB_PATH)  # development: an instrumented build of the same library
+    path = LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: run `python -m mpp_cnn_rs_object_detection_b200.build` "
                            f"(the MPP sampler has no CPU fallback)")
@@ -102,10 +111,12 @@ def load():
     lib.mpp_run_windows.argtypes = [vp, i32, i32, i32, i32, f64, f64, f64, u64, u64, C.POINTER(C.c_ulonglong), vp]
     lib.mpp_run_window_rows.argtypes = [vp, i32, i32, f64, u64, u64, i32, i32, i32]
     lib.mpp_window_grid.argtypes = [vp, u64, u64, C.POINTER(i32), C.POINTER(i32)]
+    lib.mpp_set_window_trace.argtypes = [vp, vp, u64, u64]
     lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")
-    sizes = [C.sizeof(ModelParams), C.sizeof(KernelParams), PROPOSAL_DTYPE.itemsize, STEP_RESULT_DTYPE.itemsize]
+    sizes = [C.sizeof(ModelParams), C.sizeof(KernelParams), PROPOSAL_DTYPE.itemsize, STEP_RESULT_DTYPE.itemsize,
+             WINDOW_TRACE_DTYPE.itemsize]
     for which, sz in enumerate(sizes):
         if lib.mpp_abi_struct_size(which) != sz:
             raise RuntimeError(f"ABI struct {which} size mismatch: C {lib.mpp_abi_struct_size(which)} vs python {sz}")

@@ -46,8 +46,11 @@ struct mpp_ctx {
     size_t plan_bytes = 0;
     int num_sms = 0;
     uint32_t window_uid_next = 0x80000000u;  // uids of objects born in mpp_run_windows: host-tracked, upper half of the uid space
+    mpp_window_trace *trace = nullptr;       // per-proposal trace of the window sampler (mpp_set_window_trace)
+    unsigned long long trace_capacity = 0, trace_sweep0 = 0;
 };
 
+#define MPP_MAX_DEVICES 64
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
 
@@ -71,6 +74,7 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
     c.m = h->m; c.k = h->k;
     c.visit_alpha = h->visit_alpha; c.visit_tfloor = h->visit_tfloor;
+    c.trace = h->trace; c.trace_capacity = h->trace_capacity; c.trace_sweep0 = h->trace_sweep0;
     return c;
 }
 
@@ -854,12 +858,13 @@ int mpp_abi_struct_size(int which) {
     case 1: return (int)sizeof(mpp_kernel_params);
     case 2: return (int)sizeof(mpp_proposal);
     case 3: return (int)sizeof(mpp_step_result);
+    case 4: return (int)sizeof(mpp_window_trace);
     default: return -1;
     }
 }
 
 int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precision, void *stream) {
-    if (!out || height <= 0 || width <= 0) return fail(MPP_ERR_INVALID, "mpp_ctx_create: bad arguments");
+    if (!out || height <= 0 || width <= 0 || device < 0 || device >= MPP_MAX_DEVICES) return fail(MPP_ERR_INVALID, "mpp_ctx_create: bad arguments");
     if (precision != MPP_PRECISION_FP32 && precision != MPP_PRECISION_FP64) return fail(MPP_ERR_INVALID, "mpp_ctx_create: precision");
     CUDA_TRY(cudaSetDevice(device));
     mpp_ctx *h = new (std::nothrow) mpp_ctx();
@@ -930,6 +935,7 @@ int mpp_ctx_reset(mpp_ctx *h, void *stream) {
     h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f;
     h->maps_set = false; h->model_set = false; h->kernels_set = false;
     h->window_uid_next = 0x80000000u;
+    h->trace = nullptr; h->trace_capacity = 0; h->trace_sweep0 = 0;
     memset(&h->m, 0, sizeof(h->m));
     memset(&h->k, 0, sizeof(h->k));
     return MPP_OK;
@@ -1319,11 +1325,13 @@ static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj,
     h->window_uid_next += (uint32_t)(n_wi * n_wj * per_visit);
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;  // wrapped: stay in the upper half
     const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * W2_SCRATCH * sizeof(R);
-    static bool configured = false;
-    if (!configured) {
+    // the shared-memory opt-in is a per-device attribute of the function (a process may hold contexts on several GPUs);
+    // setting it twice from two threads is harmless
+    static bool configured[MPP_MAX_DEVICES] = {};
+    if (!configured[h->device]) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep2<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[h->device] = true;
     }
     k_sweep2<R, NW, DBG, SIMT><<<n_wi * n_wj, 32 * NW, smem, h->stream>>>(device_view<R>(h), ci, cj, n_wi, n_wj, ox, oy, per_visit, temp, seed, sweep_id,
                                                                   uid_base, dbg);
@@ -1373,19 +1381,21 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     h->window_uid_next += (uint32_t)total * (uint32_t)per_visit;
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;
     const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * W2_SCRATCH * sizeof(R);
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
+    static int blocks_per_sm_dev[MPP_MAX_DEVICES] = {};  // per device: shared-memory opt-in + occupancy of this instantiation
+    if (!blocks_per_sm_dev[h->device]) {
+        int bps = 0;
         CUDA_TRY(cudaFuncSetAttribute(k_windows_dataflow<R, NW, DBG, SIMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_windows_dataflow<R, NW, DBG, SIMT>, 32 * NW, smem));
-        if (blocks_per_sm < 1) return fail(MPP_ERR_CUDA, "k_windows_dataflow does not fit on an SM");
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_windows_dataflow<R, NW, DBG, SIMT>, 32 * NW, smem));
+        if (bps < 1) return fail(MPP_ERR_CUDA, "k_windows_dataflow does not fit on an SM");
+        blocks_per_sm_dev[h->device] = bps;
     }
+    const int blocks_per_sm = blocks_per_sm_dev[h->device];
     // persistent grid: never more CTAs than fit on the device (only CTAs that are running claim tasks, so the in-order
     // queue cannot deadlock), and not many more than can ever be active at once (about two colour classes of windows),
     // so that small scenes leave room for other contexts' kernels running concurrently on other streams (waiting CTAs
     // occupy SM slots: 32 tiles of 512^2 ran at 46 M proposals/s with two colour classes of CTAs each, 103 M/s with half a class)
     const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
-    static const int cap_x4 = SIMT ? (getenv("MPP_GRID_CAP_X4_SIMT") ? atoi(getenv("MPP_GRID_CAP_X4_SIMT")) : 8)
-                                   : (getenv("MPP_GRID_CAP_X4") ? atoi(getenv("MPP_GRID_CAP_X4")) : 2);  // grid <= cap/4 colour classes + 8
+    const int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
     const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_x4 * per_colour / 4 + 8));
     k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
@@ -1490,6 +1500,12 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
         }
         if (e != cudaSuccess) return fail(MPP_ERR_CUDA, std::string("k_sweep2 launch: ") + cudaGetErrorString(e));
     }
+    return MPP_OK;
+}
+
+extern "C" int mpp_set_window_trace(mpp_ctx *h, mpp_window_trace *buf, uint64_t capacity, uint64_t sweep0) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_set_window_trace: null context");
+    h->trace = buf; h->trace_capacity = buf ? capacity : 0; h->trace_sweep0 = sweep0;
     return MPP_OK;
 }
 

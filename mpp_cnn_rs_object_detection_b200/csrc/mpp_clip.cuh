@@ -49,7 +49,7 @@ template <typename R>
 MPP_HD R quad_box_area(const R *qx, const R *qy, R hl, R hw) {
     const R ihl = rcp(hl), ihw = rcp(hw);
     const R tiny = sizeof(R) == 4 ? (R)1e-5 : (R)1e-12;
-    R sum = 0;
+    R sum = 0, plen = 0;  // plen: total (L1) length of the pieces of the quad's edges inside the box
     bool have = false;
     int k_prev = 0, k_first = 0;
     R ex = 0, ey = 0, sx0 = 0, sy0 = 0;           // last exit point, first entry point
@@ -83,9 +83,14 @@ MPP_HD R quad_box_area(const R *qx, const R *qy, R hl, R hw) {
             have = true; k_first = k; sx0 = sx; sy0 = sy; first_at_vertex = s_vertex;
         }
         sum += (R)0.5 * (sx * fy - fx * sy);
+        plen += (t1 - t0) * (ab(dx) + ab(dy));
         ex = fx; ey = fy; k_prev = k; prev_at_vertex = e_vertex;
     }
-    if (!have) {
+    // An edge that only grazes the box (a corner of the box on an edge of the quad, within rounding) leaves a piece of
+    // rounding-level length whose exit and entry coincide: the arc between them is then either nothing or the whole
+    // perimeter, which the perimeter coordinate cannot tell apart.  Pieces that short carry no area themselves, so the case is
+    // decided like "no piece at all".
+    if (!have || plen < (sizeof(R) == 4 ? (R)1e-4 : (R)1e-10)) {
         // no edge of the quad meets the box: the box is inside the quad (its centre is) or they are disjoint
         bool inside = true;
 #pragma unroll

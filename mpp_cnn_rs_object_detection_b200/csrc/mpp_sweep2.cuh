@@ -321,6 +321,21 @@ __device__ __forceinline__ float visit_temp(const Ctx<R> &c, float temp, int it)
     return fmaxf(temp * __powf(c.visit_alpha, (float)it), fminf(temp, c.visit_tfloor));
 }
 
+// one record of the per-proposal trace (mpp_window_trace, include/mpp_b200.h); called by one lane
+template <typename R>
+__device__ __forceinline__ void trace_write(mpp_window_trace *tr, uint32_t flags, int kernel, int n_win, int pid, uint32_t rem_uid, uint32_t add_uid,
+                                            const Cand<R> &a, float de, float log_ratio, float temp, uint32_t qk, uint32_t qp, uint32_t qa) {
+    mpp_window_trace t;
+    t.flags = MPP_TRACE_WRITTEN | flags | ((uint32_t)kernel << 8) | ((uint32_t)min(n_win, 255) << 16) | ((uint32_t)pid << 24);
+    t.rem_uid = rem_uid; t.add_uid = add_uid;
+    const bool ha = (flags & MPP_TRACE_HAS_ADD) != 0;
+    t.add_cls = ha ? a.cls : 0u; t.add_x = a.x; t.add_y = a.y;  // (a rejected move still reports its end point)
+    t.add_size = ha ? (float)a.size : 0.f; t.add_ratio = ha ? (float)a.ratio : 0.f; t.add_angle = ha ? (float)a.angle : 0.f;
+    t.delta_e = de; t.log_ratio = log_ratio; t.temperature = temp; t.u_accept = u01f(qa);
+    t.q[0] = qk; t.q[1] = qp; t.q[2] = qa;
+    *tr = t;
+}
+
 template <typename R>
 struct Eval {  // outcome of evaluating one proposal (warp-uniform)
     int kernel, r;
@@ -332,7 +347,7 @@ struct Eval {  // outcome of evaluating one proposal (warp-uniform)
 // Draws and evaluates proposal number `it` of this window's chain against the staged state (read-only).
 template <typename R, bool DBG>
 __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
-                                  float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff) {
+                                  float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff, mpp_window_trace *tr) {
     // random words and kernel of proposal `it`: drawn ahead by predraw_births (same counter-based stream)
     const uint4 q0 = make_uint4(w.pq[0][it], w.pq[1][it], w.pq[2][it], w.pq[3][it]);
     const uint4 q1 = make_uint4(w.pq[4][it], w.pq[5][it], w.pq[6][it], w.pq[7][it]);
@@ -350,9 +365,14 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     }
     e->r = r;
     Cand<R> &a = e->a;
+    if (DBG) { a.x = -1; a.y = -1; }
     float log_ratio = 0.f;  // log(bwd) - log(fwd)
     bool valid = true;
     float pn[3], dm[3];
+    int pid_t = 0;  // (trace) mark index of a mark transform
+    const uint32_t ruid_t = r >= 0 ? w.uid[r] : 0u, auid_t = w.uid_base + (uint32_t)it;
+    const uint32_t rem_t = r >= 0 ? MPP_TRACE_HAS_REM : 0u;
+    const float temp_it = visit_temp(c, temp, it);
     switch (kernel) {
     case 0: {  // uniform birth in the window (candidate drawn ahead)
         const float fwd = pk_of(w, 0, nc) / w.lam_unif;
@@ -387,9 +407,10 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         box_muller_f(q0.z, q0.w, &d0, &d1);
         const int nx_ = min(max((int)((float)w.x[r] + d0 * (float)c.k.trl_sigma), 0), c.H - 1);
         const int ny_ = min(max((int)((float)w.y[r] + d1 * (float)c.k.trl_sigma), 0), c.W - 1);
+        a.x = nx_; a.y = ny_;
         if (nx_ < w.x0 || nx_ >= w.x1 || ny_ < w.y0 || ny_ >= w.y1) { valid = false; break; }
         if (nx_ == w.x[r] && ny_ == w.y[r]) { e->noop = true; break; }  // the shift rounds to zero
-        a.x = nx_; a.y = ny_; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
         e->has_add = true;
         break;
@@ -406,9 +427,10 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         const float dv = lane < Y1 - Y0 ? __ldg(c.det + (size_t)(X0 + row) * c.W + Y0 + lane) : 0.f;
         const int col = warp_pick_ni(dv, u01f(q0.w), lane, nullptr);
         const int ex = X0 + row, ey = Y0 + col;
+        a.x = ex; a.y = ey;
         if (ex < w.x0 || ex >= w.x1 || ey < w.y0 || ey >= w.y1) { valid = false; break; }
         if (ex == w.x[r] && ey == w.y[r]) { e->noop = true; break; }  // the object's own pixel was drawn
-        a.x = ex; a.y = ey; a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
+        a.cls = w.cls[r]; a.size = w.size[r]; a.ratio = w.ratio[r]; a.angle = w.angle[r];
         // backward window (around the end point) + the maps at the end point, one round trip
         const int BX0 = max(0, ex - md), BX1 = min(ex + md + 1, c.H), BY0 = max(0, ey - md), BY1 = min(ey + md + 1, c.W);
         float rb = 0.f;
@@ -422,6 +444,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     }
     default: {  // 6: gaussian mark transform (symmetric), 7: data-driven mark transform
         const int pid = min(2, (int)(u01f(q0.z) * 3.0f));
+        pid_t = pid;
         const float v = __ldg(mark_row(c, pid, w.x[r], w.y[r]) + lane);
         float s;
         int ncls;
@@ -457,12 +480,18 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         break;
     }
     }
-    if (!valid) { e->has_add = false; return; }
+    if (!valid) {
+        e->has_add = false;
+        if (DBG && tr && lane == 0) trace_write<R>(tr, rem_t | MPP_TRACE_LEFT_WINDOW, kernel, nc, pid_t, ruid_t, auid_t, a, 0.f, 0.f, temp_it, q0.x, q0.y, q1.w);
+        return;
+    }
     if (e->noop) {
         // The proposal maps the configuration onto itself: Delta-energy 0 and equal forward / backward densities, so the Green
         // ratio is 1 and the reference accepts it (replacing the object by an equal one).  It counts as evaluated and accepted,
         // but there is nothing to commit, and later proposals evaluated against the same state in this round stay valid.
         e->has_add = false; e->evaluated = true; e->accept = true;
+        if (DBG && tr && lane == 0)
+            trace_write<R>(tr, rem_t | MPP_TRACE_EVALUATED | MPP_TRACE_ACCEPT | MPP_TRACE_IDENTITY, kernel, nc, pid_t, ruid_t, auid_t, a, 0.f, 0.f, temp_it, q0.x, q0.y, q1.w);
         return;
     }
     if (e->has_add) {
@@ -489,7 +518,11 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
         uint32_t dmk = w.cmask[ci];
         if (r >= 0 && w.handle[r] != MPP_NO_OBJECT && (int)(w.handle[r] >> 5) == w.ccell[ci]) dmk &= ~(1u << (w.handle[r] & 31));
-        if (dmk == 0xffffffffu) { e->has_add = false; return; }
+        if (dmk == 0xffffffffu) {
+            e->has_add = false;
+            if (DBG && tr && lane == 0) trace_write<R>(tr, rem_t | MPP_TRACE_HAS_ADD | MPP_TRACE_CELL_FULL, kernel, nc, pid_t, ruid_t, auid_t, a, 0.f, 0.f, temp_it, q0.x, q0.y, q1.w);
+            return;
+        }
     }
     const R de = delta_staged(m, w, r, e->has_add, a, lane, sx, sy, po, pa);
 #ifndef MPP_TRACE
@@ -499,10 +532,12 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (lane == 0) atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
     }
 #endif
-    const float la = -(float)de / visit_temp(c, temp, it) + log_ratio;
+    const float la = -(float)de / temp_it + log_ratio;
     e->evaluated = true;
     e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
-
+    if (DBG && tr && lane == 0)
+        trace_write<R>(tr, rem_t | (e->has_add ? MPP_TRACE_HAS_ADD : 0u) | MPP_TRACE_EVALUATED | (e->accept ? MPP_TRACE_ACCEPT : 0u), kernel, nc, pid_t, ruid_t,
+                       auid_t, a, (float)de, log_ratio, temp_it, q0.x, q0.y, q1.w);
 }
 
 // Applies an accepted proposal to the staged state and writes the new record (executed by the warp that evaluated it:
@@ -1034,23 +1069,25 @@ template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return 
 // group of G lanes (it < 0: idle group).  Returns the accept decision; *evaluated as in evaluate_proposal.
 template <typename R, bool DBG>
 __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinState<R> &w, int it, int G, float temp, int lane, R *sx, R *sy, Cand<R> *out,
-                                                  bool *evaluated, int *kernel_out, const int *near, int n_near, float *dbg_maxdiff) {
+                                                  bool *evaluated, int *kernel_out, const int *near, int n_near, float *dbg_maxdiff, mpp_window_trace *tr) {
     const ModelDev &m = c.m;
     const int j = lane & (G - 1);
     bool live = it >= 0;
     int kernel = 0;
     Cand<R> &a = *out;
+    bool full_t = false;
     if (live) {
         kernel = w.pkern[0][it];
         if (kernel == 2 && !(w.win_mass > 0.0)) live = false;
     }
+    const bool drawn_t = live;
     if (live) {
         a.x = w.pc_x[0][it]; a.y = w.pc_y[0][it]; a.cls = w.pc_cls[0][it];
         a.size = w.pc_size[0][it]; a.ratio = w.pc_ratio[0][it]; a.angle = w.pc_angle[0][it];
         a.hl = w.pc_hl[0][it]; a.hw = w.pc_hw[0][it]; a.ca = w.pc_ca[0][it]; a.sa = w.pc_sa[0][it];
         a.pos = w.pc_pos[0][it]; a.dm0 = w.pc_dm0[0][it]; a.dm1 = w.pc_dm1[0][it]; a.dm2 = w.pc_dm2[0][it];
         a.detv = w.pc_detv[0][it]; a.pn0 = w.pc_pn0[0][it]; a.pn1 = w.pc_pn1[0][it]; a.pn2 = w.pc_pn2[0][it];
-        if (w.cmask[((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0)] == 0xffffffffu) live = false;  // destination storage cell full
+        if (w.cmask[((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0)] == 0xffffffffu) { live = false; full_t = true; }  // destination storage cell full
     }
     *kernel_out = kernel;
     // Delta-energy: the objects whose reductions the new object changes, spread over the lanes of the group
@@ -1074,7 +1111,12 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
         al_add = r_max(al_add, __shfl_xor_sync(MPP_FULL, al_add, off));
     }
     *evaluated = live;
-    if (!live) return false;
+    if (!live) {
+        if (DBG && tr && it >= 0 && j == 0)
+            trace_write<R>(tr + it, (drawn_t ? MPP_TRACE_HAS_ADD : 0u) | (full_t ? MPP_TRACE_CELL_FULL : MPP_TRACE_LEFT_WINDOW), w.pkern[0][it], 0, 0, 0u,
+                           w.uid_base + (uint32_t)it, a, 0.f, 0.f, visit_temp(c, temp, it), w.pq[0][it], w.pq[1][it], w.pq[7][it]);
+        return false;
+    }
     Terms<R> t;
     t.pos = a.pos;
     shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
@@ -1091,7 +1133,11 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
     const float fwd = kernel == 0 ? pk_of(w, 0, 0) / w.lam_unif : pk_of(w, 2, 0) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2) / w.lam_data;
     const float bwd = pk_of(w, kernel + 1, 1);  // / (nc + 1) = 1
     const float log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
-    return __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / visit_temp(c, temp, it) + log_ratio;
+    const bool accept = __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / visit_temp(c, temp, it) + log_ratio;
+    if (DBG && tr && j == 0)
+        trace_write<R>(tr + it, MPP_TRACE_HAS_ADD | MPP_TRACE_EVALUATED | (accept ? MPP_TRACE_ACCEPT : 0u), kernel, 0, 0, 0u, w.uid_base + (uint32_t)it, a,
+                       (float)de, log_ratio, visit_temp(c, temp, it), w.pq[0][it], w.pq[1][it], w.pq[7][it]);
+    return accept;
 }
 
 // the speculative rounds of one visit in SIMT mode (one warp)
@@ -1285,6 +1331,13 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     __syncthreads();
     MPP_MARK(4);
 
+    // per-proposal trace (debug instantiation): records of this visit, see mpp_window_trace
+    mpp_window_trace *tr = nullptr;
+    if (DBG && c.trace && sweep_id >= c.trace_sweep0) {
+        const unsigned long long first = ((sweep_id - c.trace_sweep0) * (unsigned long long)((c.nx + 2) * (c.ny + 2)) +
+                                          (unsigned long long)(wi * (c.ny + 2) + wj)) * (unsigned long long)per_visit;
+        if (first + (unsigned long long)per_visit <= c.trace_capacity) tr = c.trace + first;
+    }
     // ------------------------------------------------------------------ speculative proposal rounds
     int it = 0;
     if (!SIMT && w.n_win == 0) {  // empty window: births only, 32 / G of them per warp at once (see evaluate_birth_group)
@@ -1310,7 +1363,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         Cand<R> a;
         bool ev = false;
         int kern = 0;
-        const bool acc = evaluate_birth_group<R, DBG>(c, w, mine < P ? mine : -1, G, temp, lane, sx, sy, &a, &ev, &kern, near, n_near, dbg_maxdiff);
+        const bool acc = evaluate_birth_group<R, DBG>(c, w, mine < P ? mine : -1, G, temp, lane, sx, sy, &a, &ev, &kern, near, n_near, dbg_maxdiff, tr);
         __syncwarp();
         const bool head = (lane & (G - 1)) == 0;
         const uint32_t bal = __ballot_sync(MPP_FULL, acc && head), evb = __ballot_sync(MPP_FULL, ev && head);
@@ -1367,7 +1420,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 #ifdef MPP_TRACE
         const long long t_a = clock64();
 #endif
-        if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff);
+        if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff, tr ? tr + mine : nullptr);
         else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.noop = false; }
         if (lane == 0) { w.res_accept[warp] = e.accept ? (e.noop ? 2 : 1) : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
         __syncthreads();

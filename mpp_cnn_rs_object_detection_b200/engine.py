@@ -375,6 +375,21 @@ class Engine:
             return out, float(dbg.cpu().item())
         return out
 
+    def trace_windows(self, n_sweeps: int, proposals_per_visit: int, sweep_offset: int = 0, **kw):
+        """run_windows(debug=True) with the per-proposal trace armed (mpp_set_window_trace).  Returns (counters, max |fast -
+        brute-force Delta E|, trace) where trace is a WINDOW_TRACE_DTYPE array of shape [n_sweeps, nx + 2, ny + 2,
+        proposals_per_visit] (entries of windows that do not exist in a sweep stay zero)."""
+        nx, ny = (self.shape[0] + 31) // 32, (self.shape[1] + 31) // 32
+        n = int(n_sweeps) * (nx + 2) * (ny + 2) * int(proposals_per_visit)
+        buf = torch.zeros((max(n, 1), _lib.WINDOW_TRACE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mpp_set_window_trace(self.ctx, buf.data_ptr(), n, int(sweep_offset)))
+        try:
+            cnt, maxdiff = self.run_windows(n_sweeps, proposals_per_visit, sweep_offset=sweep_offset, debug=True, **kw)
+        finally:
+            _lib.check(self.lib.mpp_set_window_trace(self.ctx, None, 0, 0))
+        tr = buf.cpu().numpy().view(_lib.WINDOW_TRACE_DTYPE).reshape(-1)[:n]
+        return cnt, maxdiff, tr.reshape(int(n_sweeps), nx + 2, ny + 2, int(proposals_per_visit))
+
     def run_window_rows(self, proposals_per_visit: int, n_warps: int, temperature: float, seed: int, sweep_id: int, ci: int,
                         row_lo: int, row_hi: int):
         """One third of a sweep (window rows wi = ci mod 3) restricted to the rows [row_lo, row_hi) (scene split across GPUs)."""
