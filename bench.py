@@ -7,7 +7,7 @@
 Workload (configs[2] of BASELINE.json): synthetic 2048x2048 DOTA-vehicle-like scene, ~2k oriented rectangles, hrcM
 energy model (legacy setup + hierarchical combinator with the shipped weights / calibration).  One *step* = one image's
 worth of sampling: `--sweeps` parallel colour sweeps, every 32-px window performing `--per-visit` local proposals per
-sweep (defaults give ~2.4 M proposals, the reference's own budget for a 2048^2 image: 81 patches x 30 257 steps).
+sweep (defaults give ~2.4 M proposals; the reference's own budget for a 2048^2 image is 64 patches x 30 257 steps = 1.94 M).
 N > 1: every rank samples its own scene (independent images -> weak scaling, no data-path collective).
 
 `value`     : proposals/s with the maps already resident in HBM (CUDA events around K steps, max over ranks).
@@ -36,9 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# DRAM bytes (read + write) per evaluated proposal of k_windows_dataflow<float,8>, from the ncu --set full capture
-# profiles/r01_prof_dataflow_raw.csv: (259.9168 + 34.889984) MB for 531 615 evaluated proposals in the launch
-NCU_DRAM_BYTES_PER_PROPOSAL = 738.1
+# ncu --set full capture of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one launch and the number of
+# proposals that launch evaluated), written next to the raw CSV by tools/ncu_traffic.py; roofline.traffic is derived from it
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+KERNEL_NAMES = ["uniform_birth", "uniform_death", "data_birth", "data_death", "gaussian_translation", "data_translation",
+                "gaussian_mark_transform", "data_mark_transform"]
 METRIC = "rjmcmc_proposals_per_sec"
 UNIT = "proposals/s"
 
@@ -75,6 +77,7 @@ def parse_args():
                          "colour-row phases) instead of one independent scene per rank; strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single-chain", action="store_true", help="skip the whole-scene single-chain CPU leg")
     return ap.parse_args()
 
 
@@ -139,12 +142,47 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ roofline
 def bytes_per_proposal(k2: float, acceptance: float, h: int, w: int, p_kernel, window: int = 17) -> float:
     """B = 8*C + 20*(1+K2) + 16*p_add + 16*p_dataBD + 8*ceil(log2 H + log2 W)*p_dataBirth
-    + 2*4*w^2*p_dataTrl + 128*p_dataTrf + 20*a   (C = 25 cells of the 5x5 block, K2 = mean objects in it)."""
+    + 2*4*w^2*p_dataTrl + 128*p_dataTrf + 20*a   (C = 25 cells of the 5x5 block, K2 = mean objects in it).  p_kernel: the
+    OBSERVED shares of the eight kernels among the evaluated proposals of the run (mpp_window_stats), not the reference
+    mixture: empty windows only propose births, which moves most of the weight onto the two cheapest terms."""
     p = np.asarray(p_kernel, dtype=np.float64)
+    p = p / max(p.sum(), 1e-300)
     p_add = 1.0 - (p[1] + p[3])
     p_data_bd = p[2] + p[3]
     return (8.0 * 25 + 20.0 * (1 + k2) + 16.0 * p_add + 16.0 * p_data_bd + 8.0 * math.ceil(math.log2(h) + math.log2(w)) * p[2]
             + 2 * 4.0 * window * window * p[5] + 128.0 * p[7] + 20.0 * acceptance)
+
+
+def ncu_traffic():
+    """(DRAM bytes per evaluated proposal, provenance) of the committed ncu capture, or (None, why)."""
+    try:
+        with open(NCU_TRAFFIC_FILE) as f:
+            t = json.load(f)
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / float(t["proposals_in_launch"]), \
+            {"file": os.path.relpath(NCU_TRAFFIC_FILE, ROOT), "source": t.get("source"), "kernel": t.get("kernel"),
+             "dram_bytes_read": t["dram_bytes_read"], "dram_bytes_write": t["dram_bytes_write"],
+             "proposals_in_launch": t["proposals_in_launch"], "l2_hit_pct": t.get("l2_hit_pct")}
+    except (OSError, KeyError, ValueError) as e:
+        return None, {"missing": f"{type(e).__name__}: {e}"}
+
+
+def proposal_mix(ks, seconds):
+    """Per-kernel tallies of the timed region (summed over ranks) -> the `proposal_mix` object of the bench line."""
+    ev_e, ev_o = np.array(ks[0:8], dtype=np.float64), np.array(ks[8:16], dtype=np.float64)
+    ac_e, ac_o = np.array(ks[16:24], dtype=np.float64), np.array(ks[24:32], dtype=np.float64)
+    ev, ac = ev_e + ev_o, ac_e + ac_o
+    tot = max(ev.sum(), 1.0)
+    return {"kernels": KERNEL_NAMES, "evaluated": [int(v) for v in ev], "accepted": [int(v) for v in ac],
+            "share": [float(v / tot) for v in ev], "reference_mixture": [1 / 18, 1 / 18, 1 / 9, 1 / 9, 1 / 9, 2 / 9, 1 / 9, 2 / 9],
+            "evaluated_in_empty_windows": int(ev_e.sum()), "share_from_empty_windows": float(ev_e.sum() / tot),
+            "evaluated_in_occupied_windows": int(ev_o.sum()),
+            "acceptance_empty_windows": float(ac_e.sum() / max(ev_e.sum(), 1.0)), "acceptance_occupied_windows": float(ac_o.sum() / max(ev_o.sum(), 1.0)),
+            "identity_accepted": int(ks[32]), "state_changing_accepted": int(ac.sum() - ks[32]),
+            "window_visits": int(ks[33]), "visits_of_empty_windows": int(ks[34]),
+            "value_occupied": float(ev_o.sum() / seconds), "value_occupied_unit": "proposals/s evaluated in windows that hold at least one object (the reference kernel mixture)",
+            "state_changing_accepts_per_s": float((ac.sum() - ks[32]) / seconds),
+            "note": "empty windows propose births only (evaluated ~96 per pass, almost all rejected at this temperature); "
+                    "`value` counts them, `value_occupied` does not"}
 
 
 def measured_peak():
@@ -156,18 +194,21 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_patches(args, device):
-    from mpp_cnn_rs_object_detection_b200 import synth
+REF_STEPS_PER_PATCH = 30000 + 2 * 128 + 1  # mpp_hrcM rjmcmc_params: burn_in + num_samples * samples_interval (+1: stopping.py:42)
+
+
+def scene_patches(objs, det, marks, limit=None):
+    """The reference's inference tiling (mpp_model.py:231-249): 256^2 patches anchored at linspace(0, size - 256, ceil(size / 256)),
+    i.e. 8 x 8 = 64 non-overlapping patches of a 2048^2 image.  Cropped on the device; only the patches are moved to the host."""
     from oracle import cpu_baseline as cb
-    objs, det, marks = synth.make_scene_torch(args.seed, (args.size, args.size), n_rect_for(args), device)
-    workers = cb.host_cores()
-    # crop on the device, move only the needed patches to the host
+    h, w = int(det.shape[0]), int(det.shape[1])
+    ax = np.linspace(0, h - cb.PATCH, max(1, math.ceil(h / cb.PATCH)), dtype=int)
+    ay = np.linspace(0, w - cb.PATCH, max(1, math.ceil(w / cb.PATCH)), dtype=int)
     patches = []
-    h = w = args.size
-    for i in range(0, h, cb.PATCH):
-        for j in range(0, w, cb.PATCH):
-            if len(patches) >= workers:
-                break
+    for i in ax:
+        for j in ay:
+            if limit is not None and len(patches) >= limit:
+                return patches
             i1, j1 = min(h, i + cb.PATCH), min(w, j + cb.PATCH)
             sel = (objs[:, 0] >= i) & (objs[:, 0] < i1) & (objs[:, 1] >= j) & (objs[:, 1] < j1)
             o = objs[sel].copy()
@@ -183,6 +224,34 @@ def make_pool(args, patches):
     return cb.PatchPool(patches, "legacy", CALIB_HRCM, "hierarchical", HRC, workers=None, t0=args.temperature, alpha_t=1.0)
 
 
+def cpu_image_legs(args, pool, patches, objs, det, marks):
+    """BASELINE.md section 3 items 3-4 on the host cores: (i) ms per image of the reference's parallel mode -- every one of the
+    image's 256^2 patches is sampled for a bounded number of steps, its measured rate is scaled to the shipped budget of 30 257
+    steps per patch and the patches are scheduled on the cores; (ii) ONE sequential chain over the whole scene on one core."""
+    from oracle import cpu_baseline as cb
+    steps = max(100, args.cpu_steps // 8)
+    t0 = time.perf_counter()
+    res = pool.run_each(patches, steps, warm=30, seed=args.seed + 5000)
+    wall = time.perf_counter() - t0
+    rates = [r[0] / r[1] for r in res]
+    t_img = cb.image_time_from_patch_rates(rates, REF_STEPS_PER_PATCH, pool.workers)
+    out = {"ms_per_image": 1e3 * t_img, "patches": len(patches), "steps_per_patch_budget": REF_STEPS_PER_PATCH,
+           "proposals_per_image": len(patches) * REF_STEPS_PER_PATCH, "cores": pool.workers,
+           "proposals_per_s_whole_image": len(patches) * REF_STEPS_PER_PATCH / t_img,
+           "per_patch_rate_min_median_max": [float(np.min(rates)), float(np.median(rates)), float(np.max(rates))],
+           "how": f"all {len(patches)} patches of the scene sampled for {steps} steps each ({wall:.1f} s wall), per-patch rate scaled to the "
+                  f"shipped budget of {REF_STEPS_PER_PATCH} steps, longest-first schedule on {pool.workers} cores (mpp_model.py:231-262)"}
+    single = None
+    if args.size <= 2048 and not args.no_single_chain:
+        n = max(50, args.cpu_steps // 16)
+        p, t, a, t_setup = cb.single_chain_whole_scene(det.cpu().numpy(), [marks[k].cpu().numpy() for k in range(3)], objs, "legacy",
+                                                        CALIB_HRCM, "hierarchical", HRC, n_steps=n, n_warm=10, seed=args.seed, t0=args.temperature)
+        single = {"value": p / t, "unit": UNIT, "cores": 1, "steps": n, "acceptance": a / max(1, p), "setup_s": t_setup,
+                  "what": f"one sequential chain over the whole {args.size}^2 scene (RJMCMC.run without patch tiling, rjmcmc.py:172-181); "
+                          "make_energies / make_kernels time reported as setup_s, not included"}
+    return out, single
+
+
 def run_reference(args):
     """The reference's CPU sampler (oracle port: the reference is pure Python and cannot travel to the GPU box) on all
     host cores, reference decomposition: one sequential chain per 256^2 patch per process."""
@@ -190,8 +259,10 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    from mpp_cnn_rs_object_detection_b200 import synth
     device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-    patches = cpu_patches(args, device)
+    objs, det, marks = synth.make_scene_torch(args.seed, (args.size, args.size), n_rect_for(args), device)
+    patches = scene_patches(objs, det, marks)
     pool = make_pool(args, patches)
     per_step = max(200, args.cpu_steps // 4)
     for _ in range(max(0, min(args.warmup, 1))):
@@ -201,6 +272,7 @@ def run_reference(args):
         p, t, _, _ = pool.run(per_step, seed=args.seed + 17 * s)
         tot_p += p
         tot_t += t
+    image, single = cpu_image_legs(args, pool, patches, objs, det, marks)
     pool.close()
     value = tot_p / tot_t
     sample = f"{pool.workers} workers x {per_step} proposals per step on distinct 256^2 patches of the scene ({args.steps} steps)"
@@ -209,6 +281,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "decomposition": "256x256 patches, one sequential chain per host core"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port", "sample": sample},
+            "ms_per_image": image["ms_per_image"], "whole_image": image, "single_chain": single,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -366,6 +439,7 @@ def run_b200(args):
     for s in range(args.warmup):
         step(s)
     run(0, 0, read_counters=True)  # reads + resets the counters
+    eng.window_stats()             # ... and the per-kernel tallies
     launches0 = eng.launches
     clocks = ClockSampler(local)
     barrier()
@@ -381,6 +455,13 @@ def run_b200(args):
     clk = clocks.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     cnt = run(0, 0, read_counters=True)
+    ks_local = eng.window_stats()
+    ks_vec = (ks_local["evaluated_empty"] + ks_local["evaluated_occupied"] + ks_local["accepted_empty"] + ks_local["accepted_occupied"] +
+              [ks_local["identity_accepted"], ks_local["visits"], ks_local["visits_empty"]])
+    if world > 1:
+        kt = torch.tensor(ks_vec, dtype=torch.float64, device=device)
+        dist.all_reduce(kt, op=dist.ReduceOp.SUM)
+        ks_vec = [float(v) for v in kt.tolist()]
     gpu_launches = eng.launches - launches0
     # a proposal = one RJMCMC step whose Delta-energy was evaluated (counter 4); attempts that end before the energy
     # evaluation (empty perturbations, moves leaving their window) are NOT counted
@@ -419,6 +500,23 @@ def run_b200(args):
             for rects, st in res:
                 tot["evaluated"] += st["evaluated"]; tot["launches"] += st["launches"]; tot["objects"] = len(rects[0])
 
+        def h2d_probe(nbytes=1 << 30, reps=4):
+            # plain pinned cudaMemcpyAsync on every rank at once: the aggregate host-to-device rate this box gives N concurrent
+            # uploaders, i.e. the ceiling of any end-to-end figure that uploads the maps
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            dev.copy_(host, non_blocking=True)
+            torch.cuda.synchronize()
+            barrier()
+            t_p = time.perf_counter()
+            for _ in range(reps):
+                dev.copy_(host, non_blocking=True)
+            torch.cuda.synchronize()
+            t_p = max_over_ranks(time.perf_counter() - t_p)
+            barrier()
+            return nbytes * reps * world / t_p / 1e9
+
+        h2d_ceiling = h2d_probe()
         e2e_steps = max(2, min(args.steps, 16))  # images per timed batch; the first upload (pipeline fill) is inside the timed region
         e2e_run(2)
         tot.update(evaluated=0, launches=0)
@@ -433,6 +531,10 @@ def run_b200(args):
         e2e = {"value": p2 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(det_h.numel() * 4 + marks_h.numel() * 4),
                "d2h_bytes_per_step": int(tot["objects"] * (4 + 8 + 24 + 4)), "steps": e2e_steps, "ms_per_image": 1e3 * t_e2e / e2e_steps,
                "objects_found": tot["objects"], "gpu_launches": int(tot["launches"]),
+               "h2d_gbs": (det_h.numel() * 4 + marks_h.numel() * 4) * e2e_steps * world / t_e2e / 1e9,
+               "h2d_ceiling_gbs": h2d_ceiling,
+               "h2d_note": "h2d_gbs: map bytes uploaded by all ranks / e2e time; h2d_ceiling_gbs: aggregate rate of a plain pinned cudaMemcpyAsync "
+                           "of 1 GiB x 4 issued by all ranks at once in this run (the platform's ceiling for N concurrent uploaders)",
                "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
                "call": "api.sample_rjmcmc_batch([ImageWMaps with pinned host maps] x steps, init_config='naive', fixed T) -> List[Rectangle] per image",
                "timer": "host wall clock around the call; whole batch incl. pipeline fill; per image: H2D of its maps (overlapped with the "
@@ -443,7 +545,10 @@ def run_b200(args):
     ncell = ((h + 31) // 32) * ((w + 31) // 32)
     k2 = 25.0 * (0.5 * (n0 + n1)) / ncell
     acc = accepted / max(1.0, proposals)
-    bpp = bytes_per_proposal(k2, acc, h, w, kernel_probabilities())
+    mix = proposal_mix(ks_vec, ms * 1e-3) if args.sampler == "windows" else None
+    observed = np.array(mix["evaluated"], dtype=np.float64) if mix and sum(mix["evaluated"]) > 0 else kernel_probabilities()
+    bpp = bytes_per_proposal(k2, acc, h, w, observed)
+    bpp_reference_mixture = bytes_per_proposal(k2, acc, h, w, kernel_probabilities())
     peak, peak_src = measured_peak()
     if args.sampler == "windows" and args.schedule == "dataflow":
         sweep_launches = args.steps  # one persistent kernel per step
@@ -451,10 +556,14 @@ def run_b200(args):
         sweep_launches = args.steps * args.sweeps * (9 if args.sampler == "windows" else args.stride * args.stride)
     achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
     per_launch = proposals / world / sweep_launches
-    traffic = NCU_DRAM_BYTES_PER_PROPOSAL * per_launch if (args.sampler == "windows" and args.schedule == "dataflow" and args.warps == 8) else None
+    traffic_pp, traffic_src = ncu_traffic()
+    traffic = traffic_pp * per_launch if (traffic_pp and args.sampler == "windows" and args.schedule == "dataflow" and args.warps == 8) else None
     roofline = {"bound": "hbm", "kernel": ("k_windows_dataflow<float,%d>" % args.warps if args.schedule == "dataflow" else "k_sweep2<float,%d>" % args.warps) if args.sampler == "windows" else "k_sweep<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per evaluated proposal x proposals of this launch)",
-                "algorithmic_bytes_per_launch": bpp * per_launch, "peak_source": peak_src, "bytes_per_proposal": bpp, "k2_objects_in_5x5": k2,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per evaluated proposal of the committed capture x proposals of this launch)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": bpp * per_launch, "peak_source": peak_src, "bytes_per_proposal": bpp,
+                "bytes_per_proposal_basis": "SURVEY 8d formula with the OBSERVED kernel shares of this run (proposal_mix.share)",
+                "bytes_per_proposal_reference_mixture": bpp_reference_mixture, "k2_objects_in_5x5": k2,
                 "proposals_per_launch": proposals / world / sweep_launches, "us_per_launch": 1e3 * ms / sweep_launches,
                 "note": "latency/parallelism-bound Markov chain: see DESIGN.md"}
 
@@ -467,31 +576,20 @@ def run_b200(args):
                        "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated (empty perturbations and moves leaving their window are not counted)", "objects_start": n0, "objects_end": n1, "acceptance": acc,
                        "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU",
                        "l2": "inputs larger than L2 (mark maps 3 x %.0f MB)" % (h * w * 32 * 4 / 1e6)},
-            "ms_per_image": ms / args.steps, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline}
+            "ms_per_image": ms / args.steps, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline,
+            "proposal_mix": mix}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline as cb
-        patches = []
-        det_c, marks_c = det, marks
-        workers = cb.host_cores()
-        for i in range(0, h, cb.PATCH):
-            for j in range(0, w, cb.PATCH):
-                if len(patches) >= workers:
-                    break
-                i1, j1 = min(h, i + cb.PATCH), min(w, j + cb.PATCH)
-                sel = (objs[:, 0] >= i) & (objs[:, 0] < i1) & (objs[:, 1] >= j) & (objs[:, 1] < j1)
-                o = objs[sel].copy()
-                o[:, 0] -= i
-                o[:, 1] -= j
-                patches.append((det_c[i:i1, j:j1].contiguous().cpu().numpy(),
-                                [marks_c[k, i:i1, j:j1].contiguous().cpu().numpy() for k in range(3)], o))
+        patches = scene_patches(objs, det, marks)
         pool = make_pool(args, patches)
         p, t, a, _ = pool.run(args.cpu_steps, warm=100, seed=args.seed)
+        image, single = cpu_image_legs(args, pool, patches, objs, det, marks)
         pool.close()
         line["cpu_baseline"] = {"value": p / t, "unit": UNIT, "cores": pool.workers, "kind": "port",
                                 "sample": f"{pool.workers} workers x {args.cpu_steps} proposals, one 256^2 patch chain each (reference decomposition), "
                                           f"T={args.temperature}, acceptance {a / max(1, p):.3f}",
-                                "per_core": p / t / pool.workers}
+                                "per_core": p / t / pool.workers, "ms_per_image": image["ms_per_image"], "whole_image": image,
+                                "single_chain": single}
     eng.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -253,6 +253,17 @@ int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_w
                     double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
                     unsigned long long *counters_host, float *debug_maxdiff);
 
+/* Per-kernel statistics of the window sampler since the last call (read and reset; synchronises).  The reference keeps the
+ * same tallies per kernel in RJMCMC.run's log (rjmcmc.py:115-156: kernel name, accepted).  out_host[MPP_WINDOW_STATS]:
+ *   [0..7]   proposals evaluated from an EMPTY window (births-only mixture), by kernel id
+ *   [8..15]  proposals evaluated from an occupied window (the reference mixture), by kernel id
+ *   [16..31] accepted, same layout
+ *   [32] accepted proposals that map the configuration onto itself, [33] window visits, [34] visits that found the window empty
+ * Kernel ids: 0 uniform birth, 1 uniform death, 2 data-driven birth, 3 data-driven death, 4 gaussian translation,
+ * 5 data-driven translation, 6 gaussian mark transform, 7 data-driven mark transform (make_kernels.py:88-144). */
+#define MPP_WINDOW_STATS 35
+int mpp_window_stats(mpp_ctx *ctx, unsigned long long *out_host);
+
 /* Per-proposal trace of the window sampler: what RJMCMC.step (rjmcmc.py:83-164) computes for one step -- the kernel
  * drawn (:88), the perturbation (:90), the Delta-energy (:93-100), the proposal densities (:102-103), the temperature and
  * the accept test (:105-113) -- written by the debug instantiation of the production kernels (mpp_run_windows with

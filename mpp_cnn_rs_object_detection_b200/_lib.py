@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmpp_b200.so")
 
 NO_OBJECT = 0xFFFFFFFF
 MAX_TERMS = 8
+WINDOW_STATS = 35
 PRECISION_FP32, PRECISION_FP64 = 0, 1
 SETUP_LEGACY, SETUP_NO_CALIBRATION, SETUP_TOY = 0, 1, 2
 COMB_RAW_SUM, COMB_HIERARCHICAL, COMB_LOGISTIC, COMB_MANUAL_HIERARCHICAL = 0, 1, 2, 3
@@ -57,7 +58,7 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
            "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid",
-           "mpp_set_window_trace"]
+           "mpp_set_window_trace", "mpp_window_stats"]
 
 _lib = None
 
@@ -112,6 +113,7 @@ def load():
     lib.mpp_run_window_rows.argtypes = [vp, i32, i32, f64, u64, u64, i32, i32, i32]
     lib.mpp_window_grid.argtypes = [vp, u64, u64, C.POINTER(i32), C.POINTER(i32)]
     lib.mpp_set_window_trace.argtypes = [vp, vp, u64, u64]
+    lib.mpp_window_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")

@@ -33,6 +33,7 @@ struct mpp_ctx {
     uint32_t *d_next_uid = nullptr;
     uint32_t *d_err = nullptr;
     unsigned long long *d_counters = nullptr;
+    unsigned long long *d_kstats = nullptr;  // [MPP_WINDOW_STATS]
     unsigned char *d_nms_state = nullptr;  // [H*W] naive-init scratch, allocated on first use
     const float *det = nullptr;
     const float *marks = nullptr;
@@ -71,7 +72,7 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.cell_cdf = h->d_cell_cdf;
     c.rowcum = h->d_rowcum;
     c.marksum = h->d_marksum;
-    c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters;
+    c.n_objects = h->d_nobj; c.next_uid = h->d_next_uid; c.err = h->d_err; c.counters = h->d_counters; c.kstats = h->d_kstats;
     c.m = h->m; c.k = h->k;
     c.visit_alpha = h->visit_alpha; c.visit_tfloor = h->visit_tfloor;
     c.trace = h->trace; c.trace_capacity = h->trace_capacity; c.trace_sweep0 = h->trace_sweep0;
@@ -886,6 +887,8 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_next_uid, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
+    CUDA_TRY(cudaMalloc(&h->d_kstats, sizeof(unsigned long long) * MPP_WINDOW_STATS));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, 128));
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
@@ -916,7 +919,7 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_marksum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
-    cudaFree(h->d_rowcount); cudaFree(h->d_plan); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_nms_state);
+    cudaFree(h->d_rowcount); cudaFree(h->d_plan); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_kstats); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
     return MPP_OK;
@@ -932,6 +935,7 @@ int mpp_ctx_reset(mpp_ctx *h, void *stream) {
     CUDA_TRY(cudaMemsetAsync(h->d_next_uid, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
     h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f;
     h->maps_set = false; h->model_set = false; h->kernels_set = false;
     h->window_uid_next = 0x80000000u;
@@ -1500,6 +1504,17 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
         }
         if (e != cudaSuccess) return fail(MPP_ERR_CUDA, std::string("k_sweep2 launch: ") + cudaGetErrorString(e));
     }
+    return MPP_OK;
+}
+
+extern "C" int mpp_window_stats(mpp_ctx *h, unsigned long long *out_host) {
+    if (!h || !out_host) return fail(MPP_ERR_INVALID, "mpp_window_stats: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<unsigned long long> tmp(MPP_WINDOW_STATS);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_kstats, sizeof(unsigned long long) * MPP_WINDOW_STATS, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < MPP_WINDOW_STATS; ++i) out_host[i] = tmp[i];
     return MPP_OK;
 }
 

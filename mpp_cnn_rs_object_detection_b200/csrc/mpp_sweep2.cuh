@@ -54,6 +54,9 @@ struct WinState {
     short winlist[W2_K];   // SIMT mode: staged indices of the alive window objects
     // speculation results, one slot per warp
     int res_accept[W2_MAXW], res_eval[W2_MAXW];
+    // per-visit statistics (mpp_window_stats): [0..15] evaluated by (window empty ? 0 : 8) + kernel, [16..31] accepted likewise,
+    // [32] identity proposals accepted, [33] visits, [34] visits that found the window empty
+    int kstat[MPP_WINDOW_STATS];
     // proposals drawn ahead (warp mode): random words of every proposal of the visit, its kernel under the two mixtures
     // (index 0: empty window, births only; 1: the reference mixture) and, where that kernel is a birth, the candidate
     uint32_t pq[8][W2_PRE];
@@ -339,6 +342,7 @@ __device__ __forceinline__ void trace_write(mpp_window_trace *tr, uint32_t flags
 template <typename R>
 struct Eval {  // outcome of evaluating one proposal (warp-uniform)
     int kernel, r;
+    int hyp;    // 0: proposed from an empty window (births-only mixture), 1: the reference mixture
     bool has_add, evaluated, accept;
     bool noop;  // accepted proposal that maps the configuration onto itself (see evaluate_proposal): nothing to commit
     Cand<R> a;
@@ -354,7 +358,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     const ModelDev &m = c.m;
     const int nc = w.n_win;
     const int hyp = nc > 0 ? 1 : 0;
-    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false; e->noop = false;
+    e->r = -1; e->has_add = false; e->evaluated = false; e->accept = false; e->noop = false; e->hyp = hyp;
     const int kernel = w.pkern[hyp][it];
     e->kernel = kernel;
     const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
@@ -1238,6 +1242,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
                 w.cmask[q] = ok ? __ldcg(c.mask + cy + cx * c.ny) : 0xffffffffu;
             }
             for (int k = 0; k < 8; ++k) w.pkf[k] = c.k.pf[k];
+            for (int k = 0; k < MPP_WINDOW_STATS; ++k) w.kstat[k] = 0;
             w.pk_e0 = c.k.pk_e0; w.pk_e2 = c.k.pk_e2;
             w.dens_scale = (float)c.H * (float)c.W * 32768.0f / c.det_sum;
             w.lam_unif = (float)(c.k.unif_scale * (double)((x1 - x0) * (y1 - y0)));
@@ -1373,7 +1378,12 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 #pragma unroll
         for (int q = 0; q < NW; ++q) first = min(first, w.res_accept[q]);
         const int used = first == 0x7fffffff ? P : first + 1;
+        if (head && mine < used && ev) {
+            atomicAdd(&w.kstat[kern], 1);
+            if (mine == first) atomicAdd(&w.kstat[16 + kern], 1);
+        }
         if (warp == 0 && lane == 0) {
+            w.kstat[34] = 1;
             int evn = 0;
             for (int q = 0; q < NW; ++q) {
                 const int cnt = min(max(used - q * L, 0), L) * G;  // lanes of warp q whose proposals were consumed
@@ -1421,7 +1431,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const long long t_a = clock64();
 #endif
         if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff, tr ? tr + mine : nullptr);
-        else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.noop = false; }
+        else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.noop = false; e.hyp = 0; e.kernel = 0; }
         if (lane == 0) { w.res_accept[warp] = e.accept ? (e.noop ? 2 : 1) : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
         __syncthreads();
 #ifdef MPP_TRACE
@@ -1431,6 +1441,11 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 #pragma unroll
         for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q] == 1) first = q;  // first accepted proposal that changes the state
         const int used = min(first + 1, min(NW, per_visit - it));  // proposals of the chain consumed by this round
+        if (lane == 0 && warp < used && e.evaluated) {
+            atomicAdd(&w.kstat[8 * e.hyp + e.kernel], 1);
+            if (e.accept && (e.noop || warp == first)) atomicAdd(&w.kstat[16 + 8 * e.hyp + e.kernel], 1);
+            if (e.accept && e.noop) atomicAdd(&w.kstat[32], 1);
+        }
         if (warp == 0 && lane == 0) {
             int ev = 0, same = 0;
             for (int q = 0; q < used; ++q) { ev += w.res_eval[q]; same += w.res_accept[q] == 2; }
@@ -1463,6 +1478,11 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
     }
 #endif
+    if (!SIMT)  // (the per-kernel statistics are kept by the warp-per-proposal mode only)
+        for (int k = threadIdx.x; k < MPP_WINDOW_STATS; k += 32 * NW) {
+            const int v = k == 33 ? 1 : w.kstat[k];
+            if (v) atomicAdd(c.kstats + k, (unsigned long long)v);
+        }
     if (threadIdx.x == 0) {
         if (w.masks_dirty) {
             __threadfence();  // records before masks: a window staging these cells must never see a mask bit without its record

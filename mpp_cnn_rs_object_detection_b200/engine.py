@@ -375,6 +375,14 @@ class Engine:
             return out, float(dbg.cpu().item())
         return out
 
+    def window_stats(self) -> dict:
+        """Per-kernel tallies of the window sampler since the last call (mpp_window_stats; reads and resets)."""
+        raw = (C.c_ulonglong * _lib.WINDOW_STATS)()
+        _lib.check(self.lib.mpp_window_stats(self.ctx, raw))
+        v = [int(x) for x in raw]
+        return {"evaluated_empty": v[0:8], "evaluated_occupied": v[8:16], "accepted_empty": v[16:24], "accepted_occupied": v[24:32],
+                "identity_accepted": v[32], "visits": v[33], "visits_empty": v[34]}
+
     def trace_windows(self, n_sweeps: int, proposals_per_visit: int, sweep_offset: int = 0, **kw):
         """run_windows(debug=True) with the per-proposal trace armed (mpp_set_window_trace).  Returns (counters, max |fast -
         brute-force Delta E|, trace) where trace is a WINDOW_TRACE_DTYPE array of shape [n_sweeps, nx + 2, ny + 2,

@@ -64,6 +64,42 @@ def crop_patches(det: np.ndarray, marks: Sequence[np.ndarray], objs: np.ndarray,
     return out
 
 
+def _single_chain(args):
+    (det, marks, objs, setup, calib, comb_kind, comb_args, n_steps, n_warm, seed, t0) = args
+    from oracle import mpp_oracle as orc
+    t_setup = time.perf_counter()
+    scene = orc.OracleScene(det, marks, setup="legacy", detection_threshold=calib["detection_threshold"],
+                            remap_coefs=calib["coefs"], remap_intercepts=calib["intercepts"],
+                            min_area=calib["min_area"], max_area=calib["max_area"])
+    comb = orc.OracleHierarchical(**comb_args)
+    sampler = orc.OracleSampler(scene, comb, [orc.ORect(*r) for r in objs], np.random.default_rng(seed), t0, 1.0)
+    t_setup = time.perf_counter() - t_setup
+    sampler.run(n_warm)
+    a0 = sampler.n_accepted
+    t = time.perf_counter()
+    sampler.run(n_steps)
+    dt = time.perf_counter() - t
+    return n_steps, dt, sampler.n_accepted - a0, t_setup
+
+
+def single_chain_whole_scene(det, marks, objs, setup, calib, comb_kind, comb_args, n_steps=300, n_warm=20, seed=0, t0=0.02):
+    """ONE sequential chain over the whole scene on one core (RJMCMC.run rjmcmc.py:172-181 without the patch tiling of
+    mpp_model.py:231-264): the data-driven birth draws from all H*W pixels (sampler2d.py:43).  Runs in a child process so that the
+    scene-sized float maps it derives are released afterwards.  Returns (proposals, seconds, accepted, setup seconds)."""
+    with mp.get_context("fork").Pool(1) as pool:
+        return pool.apply(_single_chain, ((det, marks, objs, setup, calib, comb_kind, comb_args, n_steps, n_warm, seed, t0),))
+
+
+def image_time_from_patch_rates(rates: Sequence[float], steps_per_patch: int, workers: int) -> float:
+    """Seconds the reference decomposition needs for one image: every patch runs `steps_per_patch` steps at its measured rate,
+    patches are handed to `workers` processes longest first (Pool.map hands them out in order; longest-first is the better case)."""
+    loads = [0.0] * max(1, workers)
+    for t in sorted((steps_per_patch / r for r in rates), reverse=True):
+        k = loads.index(min(loads))
+        loads[k] += t
+    return max(loads)
+
+
 class PatchPool:
     """A pool of worker processes, one 256^2 patch chain each (mpp_model.py:262 `_map_to_images(multiprocess=True)`)."""
 
@@ -81,6 +117,14 @@ class PatchPool:
                 for k, (d, m, o) in enumerate(self.patches)]
         res = self.pool.map(_chain, jobs, chunksize=1) if self.pool else [_chain(j) for j in jobs]
         return (sum(r[0] for r in res), max(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res))
+
+    def run_each(self, patches, steps_per_patch: int, warm: int = 0, seed: int = 0):
+        """Every patch of `patches` (any number; the pool works through them) for `steps_per_patch` steps: list of
+        (proposals, seconds, accepted, objects) per patch."""
+        setup, calib, kind, cargs = self.model
+        jobs = [(d, m, o, setup, calib, kind, cargs, steps_per_patch, warm, seed + k, self.t0, self.alpha_t)
+                for k, (d, m, o) in enumerate(patches)]
+        return self.pool.map(_chain, jobs, chunksize=1) if self.pool else [_chain(j) for j in jobs]
 
     def close(self):
         if self.pool:

@@ -168,7 +168,8 @@ class WindowOracle:
         self.rowcum = np.concatenate([np.zeros((self.H, 1)), np.cumsum(self.det64, axis=1)], axis=1)
         self.total_mass = float(self.det64.sum())
         self.stats = dict(proposals=0, evaluated=0, accepted=0, identity=0, left_window=0, borderline=0, empty_window=0, slivers=0,
-                          max_de_err=0.0, max_lr_err=0.0, per_kernel=[0] * 8, accepted_per_kernel=[0] * 8)
+                          max_de_err=0.0, max_lr_err=0.0, per_kernel=[0] * 8, accepted_per_kernel=[0] * 8,
+                          evaluated_empty=[0] * 8, evaluated_occupied=[0] * 8, accepted_empty=[0] * 8, accepted_occupied=[0] * 8)
 
     # ---- helpers
     def pk(self, k: int, n: int) -> float:
@@ -418,6 +419,7 @@ class WindowOracle:
                     self._fail(where, "identity proposal not accepted as such")
                 st["evaluated"] += 1; st["accepted"] += 1; st["identity"] += 1
                 st["accepted_per_kernel"][kernel] += 1
+                st["evaluated_occupied"][kernel] += 1; st["accepted_occupied"][kernel] += 1
                 continue
             if flags & W_IDENTITY or not flags & W_EVALUATED:
                 self._fail(where, f"flags {flags:#x}: expected an evaluated proposal")
@@ -460,9 +462,11 @@ class WindowOracle:
             elif dev_acc != (logu < la):
                 self._fail(where, f"decision {dev_acc}, oracle log u = {logu} vs log alpha = {la} (kernel {kernel})")
             st["evaluated"] += 1
+            st["evaluated_occupied" if nc > 0 else "evaluated_empty"][kernel] += 1
             if dev_acc:
                 st["accepted"] += 1
                 st["accepted_per_kernel"][kernel] += 1
+                st["accepted_occupied" if nc > 0 else "accepted_empty"][kernel] += 1
                 if rem is not None:
                     self.state.remove(rem)
                     del self.by_uid[rem.uid]

@@ -50,6 +50,10 @@ def _run(cfg, shape, n_rect, n_sweeps, per_visit, n_warps, schedule, t0, alpha_t
     st = oracle.replay(trace)
     # the device counters and the final configuration agree with the replayed chain
     assert st["proposals"] == cnt[0] and st["evaluated"] == cnt[4] and st["accepted"] == cnt[1], (st, cnt)
+    ks = eng.window_stats()  # the per-kernel tallies bench.py reports (mpp_window_stats)
+    for key in ("evaluated_empty", "evaluated_occupied", "accepted_empty", "accepted_occupied"):
+        assert ks[key] == st[key], (key, ks[key], st[key])
+    assert ks["identity_accepted"] == st["identity"]
     _, xy, mk, u = eng.read_objects()
     order = np.argsort(u)
     want = oracle.configuration()
