@@ -73,8 +73,10 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=4000, help="proposals per CPU worker in the cpu_baseline sample")
     ap.add_argument("--split", action="store_true",
-                    help="BASELINE configs[3]: ONE scene split into row bands across the ranks (halo exchange over NCCL between "
-                         "colour-row phases) instead of one independent scene per rank; strong scaling")
+                    help="BASELINE configs[3] alone: ONE scene split into row bands across the ranks (peer access over NVLink); strong scaling")
+    ap.add_argument("--split-size", type=int, default=8192, help="side of the scene of the split-scene record (BASELINE configs[3])")
+    ap.add_argument("--split-n-rect", type=int, default=0, help="candidate rectangles of that scene (0: 33000 per 8192^2 -> ~30k objects)")
+    ap.add_argument("--no-split", action="store_true", help="skip the split-scene sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single-chain", action="store_true", help="skip the whole-scene single-chain CPU leg")
@@ -287,14 +289,103 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ product arm
-def run_split(args):
-    """One scene split across the ranks (BASELINE configs[3])."""
+def hrcm_spec():
+    from mpp_cnn_rs_object_detection_b200.engine import ModelSpec
+    return ModelSpec(setup="legacy", pos_threshold=CALIB_HRCM["detection_threshold"], remap_coefs=CALIB_HRCM["coefs"],
+                     remap_intercepts=CALIB_HRCM["intercepts"], min_area=CALIB_HRCM["min_area"], max_area=CALIB_HRCM["max_area"],
+                     combinator="hierarchical",
+                     comb_w=list(HRC["weights_data"]) + list(HRC["weights_prior"]) + list(HRC["data_prior_weights"]) + [0.0],
+                     comb_bias=HRC["bias"], comb_threshold=HRC["detection_threshold"])
+
+
+def split_record(args, world, rank, device, dist):
+    """BASELINE configs[3]: ONE dense scene (default 8192^2, ~30k objects) split into `world` row bands, one per GPU; every rank
+    runs the persistent dataflow kernel over its band with peer access (NVLink P2P through CUDA IPC mappings) to the boundary
+    cells of its neighbours -- no exchange step, no collective on the data path.  Band-local maps.  world == 1: the same scene on
+    one GPU with mpp_run_windows (the strong-scaling reference).  Returns the sub-record (identical on every rank)."""
     import torch
-    import torch.distributed as dist
 
     from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg, synth
-    from mpp_cnn_rs_object_detection_b200.engine import Engine, ModelSpec
+    from mpp_cnn_rs_object_detection_b200.engine import Engine
 
+    h = w = args.split_size
+    n_rect = args.split_n_rect or int(round(33000 * (h * w) / (8192.0 * 8192.0)))
+    m0, m1 = mg.PeerSplitScene.map_rows(h, rank, world) if world > 1 else (0, h)
+    t_gen = time.perf_counter()
+    objs, det, marks = synth.make_scene_band_torch(args.seed, (h, w), n_rect, device, row0=m0, rows=m1 - m0)
+    det_sum = float(np.sum(det))
+    t_gen = time.perf_counter() - t_gen
+    eng = Engine((h, w), device=device)
+    det_band = torch.as_tensor(det[m0:m1]).to(device)
+    if world > 1:
+        eng.set_maps_band(det_band, marks, m0, det_sum)
+    else:
+        eng.set_maps(det_band, marks, det_sum=det_sum)
+    eng.set_model(hrcm_spec())
+    eng.set_kernels(intensity=max(1, len(objs)))
+    uid = np.arange(len(objs))
+    scene = mg.PeerSplitScene(eng, h, rank, world)
+    sel = scene.select_initial(objs[:, :2]) if world > 1 else np.ones(len(objs), dtype=bool)
+    eng.add_objects(objs[sel, :2], objs[sel, 2:5], uid=uid[sel])
+    if world > 1:
+        scene.attach_dist()
+
+    def step(k):
+        if world > 1:
+            scene.run(args.sweeps, args.per_visit, args.warps, args.temperature, args.seed, sweep_offset=k * args.sweeps)
+        else:
+            eng.run_windows(args.sweeps, args.per_visit, args.warps, t0=args.temperature, seed=args.seed, sweep_offset=k * args.sweeps,
+                            read_counters=False)
+
+    steps, warm = max(2, min(args.steps, 5)), max(1, min(args.warmup, 3))
+    for k in range(warm):
+        step(k)
+    torch.cuda.synchronize()
+    eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)  # reads + resets the counters
+    eng.window_stats()
+    launches0 = eng.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(steps):
+        step(warm + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    cnt = eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)
+    n_end = len(eng)
+    t = torch.tensor([float(cnt[4]), float(cnt[0]), float(cnt[1]), float(n_end), float(eng.launches - launches0)], dtype=torch.float64, device=device)
+    tm = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    proposals, attempted, accepted, objects_end, launches = (float(v) for v in t.tolist())
+    rec = {"workload": f"synthetic {h}x{w} dense scene, {len(objs)} objects at start (band generator, seed {args.seed}), hrcM energies, fixed T={args.temperature}, "
+                       f"ONE scene split into {world} row band(s)",
+           "value": proposals / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warm,
+           "ms_per_step": ms / steps, "ms_per_image": ms / steps, "proposals_per_step": proposals / steps,
+           "acceptance": accepted / max(1.0, proposals), "objects_start": len(objs), "objects_end": objects_end,
+           "gpu_launches": int(launches), "launches_per_step_per_rank": launches / steps / world,
+           "band_rows": [list(b) for b in mg.row_bands(h, world)], "map_rows_this_rank": [m0, m1],
+           "map_bytes_this_rank": int(marks.numel() * 4 + det_band.numel() * 4),
+           "transport": ("none (single GPU, mpp_run_windows dataflow schedule)" if world == 1 else
+                         "NVLink P2P loads/stores of the neighbour bands' boundary cells inside k_windows_multi (CUDA IPC mappings); "
+                         "completion stamps by st.release.sys into the neighbour's grid; no collective, no host synchronisation on the data path"),
+           "timing": "CUDA events on each rank's stream around the timed steps, max over ranks", "scene_build_s": t_gen}
+    if world > 1:
+        scene.detach()
+    eng.close()
+    del marks, det_band
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_split(args):
+    """`bench.py --split`: the split-scene record alone, as the bench line (BASELINE configs[3])."""
+    import torch
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,72 +393,15 @@ def run_split(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    h = w = args.size
-    objs, det, marks = synth.make_scene_torch(args.seed, (h, w), n_rect_for(args), device)  # same scene on every rank
-    spec = ModelSpec(setup="legacy", pos_threshold=CALIB_HRCM["detection_threshold"], remap_coefs=CALIB_HRCM["coefs"],
-                     remap_intercepts=CALIB_HRCM["intercepts"], min_area=CALIB_HRCM["min_area"], max_area=CALIB_HRCM["max_area"],
-                     combinator="hierarchical",
-                     comb_w=list(HRC["weights_data"]) + list(HRC["weights_prior"]) + list(HRC["data_prior_weights"]) + [0.0],
-                     comb_bias=HRC["bias"], comb_threshold=HRC["detection_threshold"])
-    eng = Engine((h, w), device=device)
-    eng.set_maps(det, marks)
-    eng.set_model(spec)
-    eng.set_kernels(intensity=max(1, len(objs)))
-    scene = mg.SplitScene(eng, h, rank, world, capacity=16384)
-    sel = scene.select_initial(objs[:, :2])
-    eng.add_objects(objs[sel, :2], objs[sel, 2:5], uid=np.arange(len(objs))[sel])
-
-    def step(k):
-        for s in range(args.sweeps):
-            if world > 1:
-                mg.sweep_dist(scene, args.per_visit, args.warps, args.temperature, args.seed, k * args.sweeps + s)
-            else:
-                for ci in range(3):
-                    scene.compute(ci, args.per_visit, args.warps, args.temperature, args.seed, k * args.sweeps + s)
-
-    for k in range(args.warmup):
-        step(k)
-    eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)  # reset counters
-    launches0 = eng.launches
     clocks = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    rec = split_record(args, world, rank, device, dist)
     clk = clocks.stop()
-    cnt = eng.run_windows(0, args.per_visit, args.warps, t0=args.temperature)
-    t = torch.tensor([ev0.elapsed_time(ev1), float(cnt[4]), float(cnt[0]), float(cnt[1]), float(len(scene.owned_objects()[0])),
-                      float(eng.launches - launches0)], dtype=torch.float64, device=device)
-    tmax = t.clone()
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    ms = float(tmax[0])
-    proposals, attempted, accepted, n_end, launches = (float(v) for v in t[1:])
-    ncell = ((h + 31) // 32) * ((w + 31) // 32)
-    bpp = bytes_per_proposal(25.0 * n_end / ncell, accepted / max(1.0, proposals), h, w, __import__("mpp_cnn_rs_object_detection_b200.engine", fromlist=["x"]).kernel_probabilities())
-    peak, peak_src = measured_peak()
-    achieved = bpp * (proposals / world) / (ms * 1e-3) / 1e9
-    line = {"metric": METRIC, "value": proposals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args) + f", ONE scene split into {world} row band(s)", "sampler": "windows",
-                       "schedule": "colours (3 halo exchanges per sweep over NCCL send/recv)", "sweeps_per_step": args.sweeps,
-                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "objects_start": len(objs), "objects_end": n_end,
-                       "acceptance": accepted / max(1.0, proposals), "attempted_per_step": attempted / args.steps,
-                       "l2": "inputs larger than L2"},
-            "ms_per_image": ms / args.steps, "e2e": None, "gpu_launches": int(launches), "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_sweep2<float,%d>" % args.warps, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_proposal": bpp}}
-    eng.close()
+    line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": rec["workload"], "sweeps_per_step": args.sweeps, "proposals_per_visit": args.per_visit,
+                                            "warps_per_window": args.warps, "l2": "inputs larger than L2"},
+            "ms_per_image": rec["ms_per_image"], "e2e": None, "gpu_launches": rec["gpu_launches"], "clocks": clk, "split": rec}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -414,11 +448,7 @@ def run_b200(args):
 
     h = w = args.size
     objs, det, marks = synth.make_scene_torch(args.seed + rank, (h, w), n_rect_for(args), device)
-    spec = ModelSpec(setup="legacy", pos_threshold=CALIB_HRCM["detection_threshold"], remap_coefs=CALIB_HRCM["coefs"],
-                     remap_intercepts=CALIB_HRCM["intercepts"], min_area=CALIB_HRCM["min_area"], max_area=CALIB_HRCM["max_area"],
-                     combinator="hierarchical",
-                     comb_w=list(HRC["weights_data"]) + list(HRC["weights_prior"]) + list(HRC["data_prior_weights"]) + [0.0],
-                     comb_bias=HRC["bias"], comb_threshold=HRC["detection_threshold"])
+    spec = hrcm_spec()
     eng = Engine((h, w), device=device)
     eng.set_maps(det, marks)
     eng.set_model(spec)
@@ -591,6 +621,11 @@ def run_b200(args):
                                 "per_core": p / t / pool.workers, "ms_per_image": image["ms_per_image"], "whole_image": image,
                                 "single_chain": single}
     eng.close()
+    del eng, det, marks
+    Engine.drain_pool()
+    torch.cuda.empty_cache()
+    if not args.no_split and args.sampler == "windows":
+        line["split"] = split_record(args, world, rank, device, dist)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

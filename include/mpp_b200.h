@@ -41,7 +41,8 @@ typedef enum {
     MPP_ERR_OUT_OF_BOUNDS = -4,/* object outside the support: point_set.py:99 assert */
     MPP_ERR_CELL_FULL = -5,    /* more than MPP_CELL_CAPACITY objects in one 32x32 cell */
     MPP_ERR_NEIGHBOURHOOD = -6,/* more than the scratch capacity of candidates around one perturbation */
-    MPP_ERR_NOT_FOUND = -7     /* removal of an unknown object: energy_point_set.py:88-100 KeyError */
+    MPP_ERR_NOT_FOUND = -7,    /* removal of an unknown object: energy_point_set.py:88-100 KeyError */
+    MPP_ERR_TIMEOUT = -8       /* split / batched sampler: a dependency never completed (a neighbour rank is not running) */
 } mpp_status;
 
 typedef enum { MPP_PRECISION_FP32 = 0, MPP_PRECISION_FP64 = 1 } mpp_precision;
@@ -151,6 +152,11 @@ int mpp_ctx_reset(mpp_ctx *ctx, void *stream);
  * float(np.sum(detection_map)) so that normalised densities match shape_samplers.py:87 bit for bit.
  * Builds the per-cell density sums used by the data-driven birth sampler (utils/sampler2d.py:5-48). */
 int mpp_set_maps(mpp_ctx *ctx, const float *det, const float *marks, double det_sum);
+/* Band-local maps of a scene split across GPUs: det_band (rows, W) and marks_band 3x(rows, W, 32) hold the scene rows
+ * [row0, row0 + rows) only (a rank needs its band plus 64 rows either side); det_sum_scene = the sum of the WHOLE detection
+ * map (the data-driven birth density and the birth intensity of a window are normalised by it, shape_samplers.py:87).  Only
+ * the window sampler may run on such a context (the global kernels of mpp_run_chain draw from the whole map). */
+int mpp_set_maps_band(mpp_ctx *ctx, const float *det_band, const float *marks_band, int row0, int rows, double det_sum_scene);
 int mpp_set_model(mpp_ctx *ctx, const mpp_model_params *model_host);
 int mpp_set_kernels(mpp_ctx *ctx, const mpp_kernel_params *kernels_host);
 
@@ -252,6 +258,40 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
 int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, int schedule, double t0,
                     double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
                     unsigned long long *counters_host, float *debug_maxdiff);
+
+/* Window sampler over a BATCH of independent scenes of equal shape on one device, or over the band of one scene that this
+ * rank owns (mpp_split_attach*), in ONE persistent dataflow launch (csrc/mpp_multi.cuh).  The reference maps independent
+ * 256x256 patches over a process pool (mpp_model.py:231-264, train_utils.py:11-18); here the window visits of all scenes are
+ * claimed from one queue in (sweep, colour, scene, window) order, so a batch of small tiles fills the GPU like one large
+ * scene.  grid_seed fixes the per-sweep grid offsets (shared by the batch), seeds_host[k] the random streams of scene k: a
+ * scene follows exactly the chain mpp_run_windows(seed) gives it when grid_seed == seeds_host[k].  The scenes must have run
+ * the same sweeps before (completion stamps are monotone and shared: reset the contexts together).  n_warps: 4 or 8.
+ * max_ctas > 0 caps the persistent grid (several batches / bands running concurrently on one device must fit together).
+ * counters_host[8]: totals over the scenes (as in mpp_run_sweeps; synchronises), may be NULL.
+ * ctxs_host: host array of contexts; the launch and its scratch live on the first context's stream. */
+int mpp_run_windows_batch(mpp_ctx **ctxs_host, const uint64_t *seeds_host, int n_scenes, uint64_t grid_seed, int n_sweeps,
+                          int proposals_per_visit, int n_warps, double t0, double alpha_t, double t_target,
+                          uint64_t sweep_offset, int max_ctas, unsigned long long *counters_host, float *debug_maxdiff);
+
+/* One scene split into row bands across GPUs (BASELINE configs[3]; the reference has no counterpart: its largest unit of
+ * work is one 256^2 patch).  Every rank creates a context of the WHOLE scene's shape, holds the objects whose 32-px cell
+ * row lies in its band [row_lo, row_hi) and samples the windows that start in it; the cells just across a band boundary are
+ * read and written in the neighbour's context through peer-mapped memory (NVLink P2P), and window completions are stamped
+ * into the neighbour's completion grid, so mpp_run_windows_batch(one scene) on every rank at once is the single-GPU chain
+ * of mpp_run_windows, bit for bit, without any exchange step.
+ *  mpp_split_export: CUDA IPC handles of this context's {occupancy masks, records, completion grid} (3 x 64 bytes) for the
+ *                    neighbour ranks (other processes).
+ *  mpp_split_attach: row band + the handles exported by the upper / lower neighbour (NULL: none, image border).
+ *  mpp_split_attach_local: the same for neighbour contexts of the same process (one process driving several GPUs with
+ *                    peer access, or several bands on one GPU in the tests).
+ * Bands are whole 32-px cell rows, at least 384 rows.  All ranks must have attached (host barrier) before any of them runs,
+ * and all must issue the same sequence of mpp_run_windows_batch calls. */
+#define MPP_IPC_HANDLE_BYTES 64
+int mpp_split_export(mpp_ctx *ctx, unsigned char *handles_host);
+int mpp_split_attach(mpp_ctx *ctx, int row_lo, int row_hi, const unsigned char *up_handles_host,
+                     const unsigned char *down_handles_host);
+int mpp_split_attach_local(mpp_ctx *ctx, int row_lo, int row_hi, mpp_ctx *up, mpp_ctx *down);
+int mpp_split_detach(mpp_ctx *ctx);
 
 /* Per-kernel statistics of the window sampler since the last call (read and reset; synchronises).  The reference keeps the
  * same tallies per kernel in RJMCMC.run's log (rjmcmc.py:115-156: kernel name, accepted).  out_host[MPP_WINDOW_STATS]:

@@ -13,11 +13,12 @@ LIB_PATH = os.path.join(PKG_DIR, "libmpp_b200.so")
 NO_OBJECT = 0xFFFFFFFF
 MAX_TERMS = 8
 WINDOW_STATS = 35
+IPC_HANDLE_BYTES = 64
 PRECISION_FP32, PRECISION_FP64 = 0, 1
 SETUP_LEGACY, SETUP_NO_CALIBRATION, SETUP_TOY = 0, 1, 2
 COMB_RAW_SUM, COMB_HIERARCHICAL, COMB_LOGISTIC, COMB_MANUAL_HIERARCHICAL = 0, 1, 2, 3
 
-ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OUT_OF_BOUNDS, ERR_CELL_FULL, ERR_NEIGHBOURHOOD, ERR_NOT_FOUND = -1, -2, -3, -4, -5, -6, -7
+ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OUT_OF_BOUNDS, ERR_CELL_FULL, ERR_NEIGHBOURHOOD, ERR_NOT_FOUND, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6, -7, -8
 
 
 class ModelParams(C.Structure):
@@ -58,7 +59,8 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_run_sweeps", "mpp_sample_births", "mpp_naive_init", "mpp_pack_rows", "mpp_unpack_rows",
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
            "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid",
-           "mpp_set_window_trace", "mpp_window_stats"]
+           "mpp_set_window_trace", "mpp_window_stats", "mpp_run_windows_batch", "mpp_split_export", "mpp_split_attach",
+           "mpp_split_attach_local", "mpp_split_detach", "mpp_set_maps_band"]
 
 _lib = None
 
@@ -88,6 +90,7 @@ def load():
     lib.mpp_ctx_destroy.argtypes = [vp]
     lib.mpp_ctx_reset.argtypes = [vp, vp]
     lib.mpp_set_maps.argtypes = [vp, vp, vp, f64]
+    lib.mpp_set_maps_band.argtypes = [vp, vp, vp, i32, i32, f64]
     lib.mpp_set_model.argtypes = [vp, C.POINTER(ModelParams)]
     lib.mpp_set_kernels.argtypes = [vp, C.POINTER(KernelParams)]
     lib.mpp_add_objects.argtypes = [vp, vp, vp, vp, vp, i32, vp]
@@ -114,6 +117,12 @@ def load():
     lib.mpp_window_grid.argtypes = [vp, u64, u64, C.POINTER(i32), C.POINTER(i32)]
     lib.mpp_set_window_trace.argtypes = [vp, vp, u64, u64]
     lib.mpp_window_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.mpp_run_windows_batch.argtypes = [C.POINTER(vp), C.POINTER(u64), i32, u64, i32, i32, i32, f64, f64, f64, u64, i32,
+                                          C.POINTER(C.c_ulonglong), vp]
+    lib.mpp_split_export.argtypes = [vp, C.c_char_p]
+    lib.mpp_split_attach.argtypes = [vp, i32, i32, C.c_char_p, C.c_char_p]
+    lib.mpp_split_attach_local.argtypes = [vp, i32, i32, vp, vp]
+    lib.mpp_split_detach.argtypes = [vp]
     lib.mpp_combine.argtypes = [C.POINTER(ModelParams), vp, i32, vp, vp, i32, vp]
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")

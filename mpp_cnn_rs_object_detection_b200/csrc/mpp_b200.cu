@@ -15,6 +15,7 @@
 #include "mpp_proposals.cuh"
 #include "mpp_chain.cuh"
 #include "mpp_sweep2.cuh"
+#include "mpp_multi.cuh"
 
 // ================================================================================================ host ctx
 struct mpp_ctx {
@@ -37,6 +38,7 @@ struct mpp_ctx {
     unsigned char *d_nms_state = nullptr;  // [H*W] naive-init scratch, allocated on first use
     const float *det = nullptr;
     const float *marks = nullptr;
+    int map_row0 = 0, map_rows = 0;     // rows of the scene the maps cover (mpp_set_maps: all; mpp_set_maps_band: a band)
     float det_sum = 0.f;
     bool maps_set = false, model_set = false, kernels_set = false;
     ModelDev m;
@@ -47,6 +49,15 @@ struct mpp_ctx {
     size_t plan_bytes = 0;
     int num_sms = 0;
     uint32_t window_uid_next = 0x80000000u;  // uids of objects born in mpp_run_windows: host-tracked, upper half of the uid space
+    // multi-scene / split-scene schedule (mpp_run_windows_batch)
+    int *d_done = nullptr;                   // [2][dg][dg] completion stamps (own cudaMalloc: exported to the neighbour ranks)
+    int sweeps_done = 0, last_ox = 0, last_oy = 0;  // sweeps stamped so far, grid offset of the last one
+    bool split = false;                      // this context holds one band of a scene (mpp_split_attach*)
+    int row_lo = 0, row_hi = 0;              // ... the pixel rows of the band
+    uint32_t *mask_up = nullptr, *mask_down = nullptr;
+    void *recs_up = nullptr, *recs_down = nullptr;
+    int *done_up = nullptr, *done_down = nullptr;
+    void *ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // peer mappings to close on detach
     mpp_window_trace *trace = nullptr;       // per-proposal trace of the window sampler (mpp_set_window_trace)
     unsigned long long trace_capacity = 0, trace_sweep0 = 0;
 };
@@ -68,7 +79,11 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.H = h->H; c.W = h->W; c.nx = h->nx; c.ny = h->ny; c.ncell = h->ncell;
     c.mask = h->d_mask;
     c.recs = reinterpret_cast<Rec<R> *>(h->d_recs);
-    c.det = h->det; c.marks = h->marks; c.det_sum = h->det_sum;
+    // band-local maps: bias the pointers so that the kernels keep indexing by scene rows
+    c.det = h->det - (ptrdiff_t)h->map_row0 * h->W;
+    c.marks = h->marks - (ptrdiff_t)h->map_row0 * h->W * MPP_N_CLASSES;
+    c.mark_plane = (size_t)(h->map_rows ? h->map_rows : h->H) * h->W * MPP_N_CLASSES;
+    c.det_sum = h->det_sum;
     c.cell_cdf = h->d_cell_cdf;
     c.rowcum = h->d_rowcum;
     c.marksum = h->d_marksum;
@@ -76,6 +91,10 @@ static Ctx<R> device_view(const mpp_ctx *h) {
     c.m = h->m; c.k = h->k;
     c.visit_alpha = h->visit_alpha; c.visit_tfloor = h->visit_tfloor;
     c.trace = h->trace; c.trace_capacity = h->trace_capacity; c.trace_sweep0 = h->trace_sweep0;
+    c.own_lo = h->split ? h->row_lo / MPP_CELL_SIZE : 0;
+    c.own_hi = h->split ? (h->row_hi + MPP_CELL_SIZE - 1) / MPP_CELL_SIZE : h->nx;
+    c.mask_up = h->mask_up; c.mask_down = h->mask_down;
+    c.recs_up = reinterpret_cast<Rec<R> *>(h->recs_up); c.recs_down = reinterpret_cast<Rec<R> *>(h->recs_down);
     return c;
 }
 
@@ -94,6 +113,7 @@ static int check_device_errors(mpp_ctx *h) {
     if (f & ERRF_OUT_OF_BOUNDS) return fail(MPP_ERR_OUT_OF_BOUNDS, "object outside the support (point_set.py:99)");
     if (f & ERRF_NOT_FOUND) return fail(MPP_ERR_NOT_FOUND, "removal of an object that is not in the set");
     if (f & ERRF_CELL_FULL) return fail(MPP_ERR_CELL_FULL, "more than 32 objects in one 32x32 cell");
+    if (f & ERRF_TIMEOUT) return fail(MPP_ERR_TIMEOUT, "a window visit waited too long for a visit it depends on (neighbour rank not running?)");
     return fail(MPP_ERR_NEIGHBOURHOOD, "more than MPP_KMAX objects around one perturbation");
 }
 
@@ -919,6 +939,8 @@ int mpp_ctx_destroy(mpp_ctx *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_mask); cudaFree(h->d_recs); cudaFree(h->d_cell_cdf); cudaFree(h->d_rowcum); cudaFree(h->d_marksum); cudaFree(h->d_scan); cudaFree(h->d_nobj);
+    for (void *p : h->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
+    cudaFree(h->d_done);
     cudaFree(h->d_rowcount); cudaFree(h->d_plan); cudaFree(h->d_next_uid); cudaFree(h->d_err); cudaFree(h->d_counters); cudaFree(h->d_kstats); cudaFree(h->d_nms_state);
     cudaFreeHost(h->h_pinned);
     delete h;
@@ -936,10 +958,15 @@ int mpp_ctx_reset(mpp_ctx *h, void *stream) {
     CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
-    h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f;
+    h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f; h->map_row0 = 0; h->map_rows = 0;
     h->maps_set = false; h->model_set = false; h->kernels_set = false;
     h->window_uid_next = 0x80000000u;
     h->trace = nullptr; h->trace_capacity = 0; h->trace_sweep0 = 0;
+    h->sweeps_done = 0; h->last_ox = 0; h->last_oy = 0;
+    for (void *&p : h->ipc_opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    h->split = false; h->row_lo = 0; h->row_hi = 0;
+    h->mask_up = h->mask_down = nullptr; h->recs_up = h->recs_down = nullptr; h->done_up = h->done_down = nullptr;
+    if (h->d_done) { const int dg = (std::max(h->H, h->W) + 31) / 32 + 2; CUDA_TRY(cudaMemsetAsync(h->d_done, 0, sizeof(int) * 2 * dg * dg, h->stream)); }
     memset(&h->m, 0, sizeof(h->m));
     memset(&h->k, 0, sizeof(h->k));
     return MPP_OK;
@@ -948,7 +975,7 @@ int mpp_ctx_reset(mpp_ctx *h, void *stream) {
 int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_sum) {
     if (!h || !det || !marks) return fail(MPP_ERR_INVALID, "mpp_set_maps: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    h->det = det; h->marks = marks;
+    h->det = det; h->marks = marks; h->map_row0 = 0; h->map_rows = h->H;
     const int blocks = (h->ncell + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     k_cell_mass<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det, h->H, h->W, h->ny, h->ncell, h->d_cell_cdf);
     k_scan_double<<<1, 1024, 0, h->stream>>>(h->d_cell_cdf, h->ncell);
@@ -967,6 +994,27 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->det_sum = (float)*tmp;
     }
+    h->maps_set = true;
+    return MPP_OK;
+}
+
+__global__ void k_set_inv_total(double *cdf, int n, double total) { cdf[n] = total > 0.0 ? 1.0 / total : 0.0; }
+
+int mpp_set_maps_band(mpp_ctx *h, const float *det_band, const float *marks_band, int row0, int rows, double det_sum_scene) {
+    if (!h || !det_band || !marks_band) return fail(MPP_ERR_INVALID, "mpp_set_maps_band: null argument");
+    if (row0 < 0 || rows < 1 || row0 + rows > h->H || !(det_sum_scene > 0.0)) return fail(MPP_ERR_INVALID, "mpp_set_maps_band: bad band or scene sum");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->det = det_band; h->marks = marks_band; h->map_row0 = row0; h->map_rows = rows;
+    k_set_inv_total<<<1, 1, 0, h->stream>>>(h->d_cell_cdf, h->ncell, det_sum_scene);
+    k_row_prefix<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, h->stream>>>(det_band, rows, h->W,
+                                                                                                       h->d_rowcum + (size_t)row0 * ((size_t)h->W + 1));
+    for (int i = 0; i < 3; ++i) {
+        const size_t n_rows = (size_t)rows * h->W, n_warps = (n_rows + 31) / 32;
+        k_mark_sums<<<(unsigned)((n_warps + 7) / 8), 256, 0, h->stream>>>(marks_band + (size_t)i * rows * h->W * MPP_N_CLASSES, n_rows,
+                                                                        h->d_marksum + (size_t)i * h->H * h->W + (size_t)row0 * h->W);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->det_sum = (float)det_sum_scene;
     h->maps_set = true;
     return MPP_OK;
 }
@@ -1064,6 +1112,8 @@ int mpp_set_kernels(mpp_ctx *h, const mpp_kernel_params *p) {
     return MPP_OK;
 }
 
+static int refresh_row_counts_impl(mpp_ctx *h);
+static int refresh_row_counts(mpp_ctx *h) { return refresh_row_counts_impl(h); }
 #define NEED(h, cond, what) do { if (!(h)) return fail(MPP_ERR_INVALID, "null ctx"); if (!(cond)) return fail(MPP_ERR_STATE, what); } while (0)
 
 int mpp_add_objects(mpp_ctx *h, const int32_t *xy, const double *marks, const uint32_t *cls, const uint32_t *uid, int n,
@@ -1098,6 +1148,10 @@ int mpp_clear_objects(mpp_ctx *h) {
 int mpp_num_objects(mpp_ctx *h, int *n_host) {
     NEED(h, n_host != nullptr, "mpp_num_objects: null output");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->split) {  // a neighbour rank's windows add to / remove from this band's boundary cells: recount from the masks
+        const int rc = refresh_row_counts(h);
+        if (rc != MPP_OK) return rc;
+    }
     CUDA_TRY(cudaMemcpyAsync(h->h_pinned, h->d_nobj, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     *n_host = *h->h_pinned;
@@ -1298,7 +1352,7 @@ int mpp_unpack_rows(mpp_ctx *h, int row_lo, int row_hi, const double *buf, int n
 
 }  // extern "C"
 
-static int refresh_row_counts(mpp_ctx *h) {
+static int refresh_row_counts_impl(mpp_ctx *h) {
     CUDA_TRY(cudaMemsetAsync(h->d_nobj, 0, sizeof(int), h->stream));
     const int blocks = (h->nx + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     k_row_counts<<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(h->d_mask, h->nx, h->ny, h->d_rowcount, h->d_nobj);
@@ -1524,6 +1578,263 @@ extern "C" int mpp_set_window_trace(mpp_ctx *h, mpp_window_trace *buf, uint64_t 
     return MPP_OK;
 }
 
+// ================================================================================================ multi-scene / split-scene schedule
+static int done_grid_pitch(const mpp_ctx *h) { return (std::max(h->H, h->W) + 31) / 32 + 2; }
+
+static int ensure_done_grid(mpp_ctx *h) {
+    if (h->d_done) return MPP_OK;
+    const int dg = done_grid_pitch(h);
+    CUDA_TRY(cudaMalloc(&h->d_done, sizeof(int) * 2 * dg * dg));
+    CUDA_TRY(cudaMemset(h->d_done, 0, sizeof(int) * 2 * dg * dg));
+    h->sweeps_done = 0;
+    return MPP_OK;
+}
+
+template <int NW, bool DBG, bool SPLIT>
+static int launch_multi(mpp_ctx **ctxs, const uint64_t *seeds, int n, uint64_t grid_seed, int n_sweeps, int per_visit, double t0, double alpha_t,
+                        double t_target, uint64_t sweep_offset, int max_ctas, float *dbg) {
+    typedef float R;
+    mpp_ctx *h0 = ctxs[0];
+    const int S = n_sweeps, H = h0->H, W = h0->W, dg = done_grid_pitch(h0);
+    std::vector<int> ints((size_t)4 * S + 2 + 9 * S + 1);
+    int *ox = ints.data(), *oy = ox + S + 1, *wlo = oy + S + 1, *whi = wlo + S, *base = whi + S;
+    std::vector<float> temps(S);
+    ox[0] = h0->last_ox; oy[0] = h0->last_oy;
+    double temp = t0;
+    long long total = 0;
+    for (int s = 0; s < S; ++s) {
+        const uint64_t hsh = splitmix64(grid_seed ^ splitmix64(sweep_offset + (uint64_t)s));
+        ox[s + 1] = (int)(hsh & 31); oy[s + 1] = (int)((hsh >> 5) & 31);
+        const int nwx = (H + ox[s + 1] + 31) / 32, nwy = (W + oy[s + 1] + 31) / 32;
+        // window rows of this rank: first pixel row max(32 wi - ox, 0) in [row_lo, row_hi)
+        wlo[s] = 0; whi[s] = nwx;
+        if (SPLIT) {
+            wlo[s] = h0->row_lo <= 0 ? 0 : (h0->row_lo + ox[s + 1] + 31) / 32;
+            whi[s] = h0->row_hi >= H ? nwx : std::min(nwx, (h0->row_hi + ox[s + 1] + 31) / 32);
+        }
+        for (int col = 0; col < 9; ++col) {
+            const int ci = col / 3, cj = col % 3;
+            const int first_i = wlo[s] + (ci - wlo[s] % 3 + 3) % 3;
+            const int a_i = first_i < whi[s] ? (whi[s] - first_i + 2) / 3 : 0, a_j = cj < nwy ? (nwy - cj + 2) / 3 : 0;
+            base[9 * s + col] = (int)total;
+            total += (long long)n * a_i * a_j;
+        }
+        temps[s] = (float)temp;
+        if (temp > t_target) temp *= alpha_t;
+    }
+    base[9 * S] = (int)total;
+    if (total > 0x7fffffffLL) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: more than 2^31 window visits in one call");
+    // scene descriptors
+    std::vector<SceneDev<R>> scenes(n);
+    for (int k = 0; k < n; ++k) {
+        mpp_ctx *h = ctxs[k];
+        SceneDev<R> &d = scenes[k];
+        memset(&d, 0, sizeof(d));
+        d.c = device_view<R>(h);
+        d.seed = seeds[k];
+        d.done = h->d_done; d.done_up = h->done_up; d.done_down = h->done_down;
+        d.notify_lo = h->row_lo + 160; d.notify_hi = h->row_hi - 160;
+    }
+    // device layout in the plan scratch of the first context: [ints | next_task | temps | scenes]
+    const size_t n_int = ints.size() + 1;
+    size_t off_temp = n_int * sizeof(int), off_scenes = (off_temp + (size_t)S * sizeof(float) + 15) & ~(size_t)15;
+    const size_t bytes = off_scenes + (size_t)n * sizeof(SceneDev<R>);
+    if (bytes > h0->plan_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(h0->stream));
+        cudaFree(h0->d_plan);
+        h0->d_plan = nullptr; h0->plan_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h0->d_plan, bytes * 2));
+        h0->plan_bytes = bytes * 2;
+    }
+    unsigned char *d_base = reinterpret_cast<unsigned char *>(h0->d_plan);
+    int *d_int = reinterpret_cast<int *>(d_base);
+    CUDA_TRY(cudaMemcpyAsync(d_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, h0->stream));
+    CUDA_TRY(cudaMemsetAsync(d_int + ints.size(), 0, sizeof(int), h0->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_base + off_temp, temps.data(), (size_t)S * sizeof(float), cudaMemcpyHostToDevice, h0->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_base + off_scenes, scenes.data(), (size_t)n * sizeof(SceneDev<R>), cudaMemcpyHostToDevice, h0->stream));
+    CUDA_TRY(cudaStreamSynchronize(h0->stream));  // the host vectors go out of scope
+    MultiPlan plan;
+    plan.n_sweeps = S; plan.n_scenes = n; plan.total_tasks = (int)total; plan.dg = dg;
+    plan.stamp0 = h0->sweeps_done + 1;
+    plan.ox = d_int; plan.oy = d_int + S + 1; plan.wi_lo = d_int + 2 * S + 2; plan.wi_hi = d_int + 3 * S + 2; plan.task_base = d_int + 4 * S + 2;
+    plan.next_task = d_int + ints.size();
+    plan.temp = reinterpret_cast<const float *>(d_base + off_temp);
+    constexpr size_t WS = (sizeof(WinState<R>) + 15) & ~(size_t)15, SC = ((size_t)NW * W2_SCRATCH * sizeof(R) + 15) & ~(size_t)15;
+    const size_t smem = WS + SC + sizeof(SceneDev<R>);
+    static int blocks_per_sm_dev[MPP_MAX_DEVICES] = {};
+    if (!blocks_per_sm_dev[h0->device]) {
+        int bps = 0;
+        CUDA_TRY(cudaFuncSetAttribute(k_windows_multi<R, NW, DBG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_windows_multi<R, NW, DBG, SPLIT>, 32 * NW, smem));
+        if (bps < 1) return fail(MPP_ERR_CUDA, "k_windows_multi does not fit on an SM");
+        blocks_per_sm_dev[h0->device] = bps;
+    }
+    // persistent grid: never more CTAs than are resident at once (only running CTAs claim visits); about half a colour class of
+    // every scene can be active at a time
+    const int rows = SPLIT ? (h0->row_hi - h0->row_lo) : H;
+    const long long per_colour = (long long)n * (((rows + 63) / 32 + 2) / 3) * (((W + 63) / 32 + 2) / 3);
+    long long grid = std::min<long long>(std::min<long long>(total, (long long)blocks_per_sm_dev[h0->device] * h0->num_sms), per_colour / 2 + 8);
+    if (max_ctas > 0) grid = std::min<long long>(grid, max_ctas);
+    grid = std::max<long long>(grid, 1);
+    if (total > 0)
+        k_windows_multi<R, NW, DBG, SPLIT><<<(int)grid, 32 * NW, smem, h0->stream>>>(reinterpret_cast<const SceneDev<R> *>(d_base + off_scenes), plan, per_visit,
+                                                                                    sweep_offset, dbg);
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < n; ++k) {
+        ctxs[k]->sweeps_done += S;
+        if (S > 0) { ctxs[k]->last_ox = ox[S]; ctxs[k]->last_oy = oy[S]; }
+    }
+    return MPP_OK;
+}
+
+extern "C" int mpp_run_windows_batch(mpp_ctx **ctxs, const uint64_t *seeds, int n_scenes, uint64_t grid_seed, int n_sweeps, int per_visit,
+                                     int n_warps, double t0, double alpha_t, double t_target, uint64_t sweep_offset, int max_ctas,
+                                     unsigned long long *counters_host, float *debug_maxdiff) {
+    if (!ctxs || !seeds || n_scenes < 1) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: no scenes");
+    if (n_sweeps < 0 || per_visit < 1 || per_visit > W2_PRE || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: bad arguments (1 <= proposals_per_visit <= 128)");
+    if (n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: n_warps must be 4 or 8");
+    mpp_ctx *h0 = ctxs[0];
+    for (int k = 0; k < n_scenes; ++k) {
+        mpp_ctx *h = ctxs[k];
+        NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_windows_batch: set maps, model and kernels of every scene first");
+        if (h->H != h0->H || h->W != h0->W || h->device != h0->device || h->precision != MPP_PRECISION_FP32 || h->m.setup == MPP_SETUP_TOY)
+            return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: scenes must share shape and device, float32 map-driven models only");
+        if (h->split && n_scenes != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: a split scene runs alone on its rank");
+    }
+    CUDA_TRY(cudaSetDevice(h0->device));
+    for (int k = 0; k < n_scenes; ++k) {
+        mpp_ctx *h = ctxs[k];
+        const int rc = ensure_done_grid(h);
+        if (rc != MPP_OK) return rc;
+        if (h->sweeps_done != h0->sweeps_done || h->last_ox != h0->last_ox || h->last_oy != h0->last_oy)
+            return fail(MPP_ERR_STATE, "mpp_run_windows_batch: the scenes of a batch must have run the same sweeps before (reset them together)");
+        h->visit_alpha = (alpha_t > 0.0 && alpha_t < 1.0) ? (float)pow(alpha_t, 1.0 / (double)per_visit) : 1.f;
+        h->visit_tfloor = (float)t_target;
+        if (h->stream != h0->stream) CUDA_TRY(cudaStreamSynchronize(h->stream));  // its maps / objects were set up on its own stream
+    }
+    int rc;
+#define MPP_LAUNCH_M(NWV, SPL) (debug_maxdiff \
+        ? launch_multi<NWV, true, SPL>(ctxs, seeds, n_scenes, grid_seed, n_sweeps, per_visit, t0, alpha_t, t_target, sweep_offset, max_ctas, debug_maxdiff) \
+        : launch_multi<NWV, false, SPL>(ctxs, seeds, n_scenes, grid_seed, n_sweeps, per_visit, t0, alpha_t, t_target, sweep_offset, max_ctas, debug_maxdiff))
+    if (h0->split) rc = n_warps == 4 ? MPP_LAUNCH_M(4, true) : MPP_LAUNCH_M(8, true);
+    else rc = n_warps == 4 ? MPP_LAUNCH_M(4, false) : MPP_LAUNCH_M(8, false);
+#undef MPP_LAUNCH_M
+    if (rc != MPP_OK) return rc;
+    if (counters_host) {
+        for (int i = 0; i < 8; ++i) counters_host[i] = 0;
+        std::vector<unsigned long long> tmp((size_t)8 * n_scenes);
+        std::vector<uint32_t> errs(n_scenes);
+        for (int k = 0; k < n_scenes; ++k) {
+            CUDA_TRY(cudaMemcpyAsync(tmp.data() + 8 * k, ctxs[k]->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, h0->stream));
+            CUDA_TRY(cudaMemsetAsync(ctxs[k]->d_counters, 0, sizeof(unsigned long long) * 8, h0->stream));
+            CUDA_TRY(cudaMemcpyAsync(&errs[k], ctxs[k]->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, h0->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(h0->stream));
+        for (int k = 0; k < n_scenes; ++k) {
+            for (int i = 0; i < 8; ++i) counters_host[i] += tmp[8 * k + i];
+            if (errs[k]) { const int e = check_device_errors(ctxs[k]); if (e != MPP_OK) return e; }
+        }
+    }
+    return MPP_OK;
+}
+
+// ---- scene split across GPUs: peer mappings of the neighbours' state
+extern "C" int mpp_split_export(mpp_ctx *h, unsigned char *handles_host) {
+    if (!h || !handles_host) return fail(MPP_ERR_INVALID, "mpp_split_export: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int rc = ensure_done_grid(h);
+    if (rc != MPP_OK) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    void *ptrs[3] = {h->d_mask, h->d_recs, h->d_done};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t hd;
+        CUDA_TRY(cudaIpcGetMemHandle(&hd, ptrs[i]));
+        memcpy(handles_host + (size_t)i * MPP_IPC_HANDLE_BYTES, &hd, MPP_IPC_HANDLE_BYTES);
+    }
+    return MPP_OK;
+}
+
+static int split_common(mpp_ctx *h, int row_lo, int row_hi) {
+    if (row_lo < 0 || row_hi > h->H || row_lo >= row_hi || row_lo % MPP_CELL_SIZE || (row_hi % MPP_CELL_SIZE && row_hi != h->H))
+        return fail(MPP_ERR_INVALID, "mpp_split_attach: the band must be a range of whole 32-px cell rows");
+    if ((row_lo > 0 || row_hi < h->H) && row_hi - row_lo < 384)
+        return fail(MPP_ERR_INVALID, "mpp_split_attach: bands must be at least 384 rows (a window only ever reaches its two neighbour bands)");
+    if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_split_attach: float32 contexts only");
+    const int rc = ensure_done_grid(h);
+    if (rc != MPP_OK) return rc;
+    // the plan scratch is allocated now: cudaFree / cudaMalloc at run time would synchronise the device while a neighbour band's
+    // kernel (same device, in the tests) is waiting for this band to start
+    const size_t want = (size_t)1 << 20;
+    if (h->plan_bytes < want) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_plan);
+        h->d_plan = nullptr; h->plan_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->d_plan, want));
+        h->plan_bytes = want;
+    }
+    h->split = true; h->row_lo = row_lo; h->row_hi = row_hi;
+    return MPP_OK;
+}
+
+extern "C" int mpp_split_attach(mpp_ctx *h, int row_lo, int row_hi, const unsigned char *up_handles_host, const unsigned char *down_handles_host) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_split_attach: null context");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = split_common(h, row_lo, row_hi);
+    if (rc != MPP_OK) return rc;
+    const unsigned char *src[2] = {up_handles_host, down_handles_host};
+    for (int side = 0; side < 2; ++side) {
+        void *opened[3] = {nullptr, nullptr, nullptr};
+        if (src[side])
+            for (int i = 0; i < 3; ++i) {
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, src[side] + (size_t)i * MPP_IPC_HANDLE_BYTES, MPP_IPC_HANDLE_BYTES);
+                CUDA_TRY(cudaIpcOpenMemHandle(&opened[i], hd, cudaIpcMemLazyEnablePeerAccess));
+                h->ipc_opened[3 * side + i] = opened[i];
+            }
+        if (side == 0) { h->mask_up = (uint32_t *)opened[0]; h->recs_up = opened[1]; h->done_up = (int *)opened[2]; }
+        else { h->mask_down = (uint32_t *)opened[0]; h->recs_down = opened[1]; h->done_down = (int *)opened[2]; }
+    }
+    return MPP_OK;
+}
+
+extern "C" int mpp_split_attach_local(mpp_ctx *h, int row_lo, int row_hi, mpp_ctx *up, mpp_ctx *down) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_split_attach_local: null context");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = split_common(h, row_lo, row_hi);
+    if (rc != MPP_OK) return rc;
+    mpp_ctx *nb[2] = {up, down};
+    for (int side = 0; side < 2; ++side) {
+        mpp_ctx *o = nb[side];
+        if (o) {
+            if (o->H != h->H || o->W != h->W || o->precision != h->precision) return fail(MPP_ERR_INVALID, "mpp_split_attach_local: neighbour of another shape");
+            rc = ensure_done_grid(o);
+            if (rc != MPP_OK) return rc;
+            if (o->device != h->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+                if (!can) return fail(MPP_ERR_CUDA, "mpp_split_attach_local: no peer access between the two devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(MPP_ERR_CUDA, cudaGetErrorString(e));
+                cudaGetLastError();
+                CUDA_TRY(cudaSetDevice(h->device));
+            }
+        }
+        if (side == 0) { h->mask_up = o ? o->d_mask : nullptr; h->recs_up = o ? o->d_recs : nullptr; h->done_up = o ? o->d_done : nullptr; }
+        else { h->mask_down = o ? o->d_mask : nullptr; h->recs_down = o ? o->d_recs : nullptr; h->done_down = o ? o->d_done : nullptr; }
+    }
+    return MPP_OK;
+}
+
+extern "C" int mpp_split_detach(mpp_ctx *h) {
+    if (!h) return fail(MPP_ERR_INVALID, "mpp_split_detach: null context");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (void *&p : h->ipc_opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    h->split = false; h->row_lo = 0; h->row_hi = 0;
+    h->mask_up = h->mask_down = nullptr; h->recs_up = h->recs_down = nullptr; h->done_up = h->done_down = nullptr;
+    return MPP_OK;
+}
+
 extern "C" int mpp_window_grid(mpp_ctx *h, uint64_t seed, uint64_t sweep_id, int *ox_host, int *oy_host) {
     if (!h || !ox_host || !oy_host) return fail(MPP_ERR_INVALID, "mpp_window_grid: null argument");
     const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
@@ -1534,6 +1845,7 @@ extern "C" int mpp_window_grid(mpp_ctx *h, uint64_t seed, uint64_t sweep_id, int
 extern "C" int mpp_run_chain(mpp_ctx *h, int n_steps, double t0, double alpha_t, double t_target, uint64_t seed, uint64_t step_offset,
                   mpp_step_result *trace, unsigned long long *counters_host) {
     NEED(h, h->maps_set && h->model_set && h->kernels_set, "mpp_run_chain: set maps, model and kernels first");
+    if (h->map_rows != h->H) return fail(MPP_ERR_STATE, "mpp_run_chain: the global kernels need the maps of the whole scene (band-local maps are set)");
     if (n_steps < 0 || !(t0 > 0.0)) return fail(MPP_ERR_INVALID, "mpp_run_chain: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
     if (n_steps > 0) {

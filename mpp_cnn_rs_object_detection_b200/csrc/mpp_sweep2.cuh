@@ -547,7 +547,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
 // Applies an accepted proposal to the staged state and writes the new record (executed by the warp that evaluated it:
 // its po / pa scratch still holds the pair values between every staged entry and the added object).  The occupancy
 // masks of the window's storage cells are only published at the end of the visit.
-template <typename R>
+template <typename R, bool SPLIT = false>
 __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy, const R *po, const R *pa) {
     const ModelDev &m = c.m;
     const int r = e.r;
@@ -589,7 +589,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
             rec.size = a.size; rec.ratio = a.ratio; rec.angle = a.angle;
             rec.e_pos = a.pos; rec.e_m[0] = w.tm0[s]; rec.e_m[1] = w.tm1[s]; rec.e_m[2] = w.tm2[s];
             rec.hl = a.hl; rec.hw = a.hw; rec.ca = a.ca; rec.sa = a.sa; rec.pad = 0;
-            store_rec(c.recs + h, rec);
+            store_rec(rec_ptr<SPLIT>(c, h), rec);
             w.cmask[ci] |= 1u << slot;
         }
     }
@@ -1193,7 +1193,7 @@ __device__ __forceinline__ void stage_sync(int n_threads) { asm volatile("bar.sy
 
 // One visit of window (wi, wj) of the grid shifted by (ox, oy): staging, `per_visit` proposals, publication.
 // `uid_first` is the uid of the first object this visit may create.  Must be called by the whole CTA.
-template <typename R, int NW, bool DBG, bool SIMT = false>
+template <typename R, int NW, bool DBG, bool SIMT = false, bool SPLIT = false>
 __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi, int wj, int ox, int oy, int per_visit, float temp,
                              uint64_t seed, uint64_t sweep_id, uint32_t uid_first, float *dbg_maxdiff) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1239,7 +1239,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
                 const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
                 const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);
                 w.ccell[q] = ok ? cy + cx * c.ny : -1;
-                w.cmask[q] = ok ? __ldcg(c.mask + cy + cx * c.ny) : 0xffffffffu;
+                w.cmask[q] = ok ? ld_state<SPLIT>(mask_ptr<SPLIT>(c, cy + cx * c.ny)) : 0xffffffffu;
             }
             for (int k = 0; k < 8; ++k) w.pkf[k] = c.k.pf[k];
             for (int k = 0; k < MPP_WINDOW_STATS; ++k) w.kstat[k] = 0;
@@ -1262,7 +1262,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             const int k = b + lane;
             int cell = 0;
             uint32_t msk = 0;
-            if (k < ncells) { cell = (sy0 + k % ncw) + (sx0 + k / ncw) * c.ny; msk = __ldcg(c.mask + cell); }
+            if (k < ncells) { cell = (sy0 + k % ncw) + (sx0 + k / ncw) * c.ny; msk = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell)); }
             uint32_t any = __ballot_sync(MPP_FULL, msk != 0);
             while (any) {
                 uint32_t h = 0;
@@ -1272,7 +1272,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
                     const int slot = __ffs(msk) - 1;
                     msk &= msk - 1;
                     h = (uint32_t)cell * 32u + slot;
-                    head = __ldcg(reinterpret_cast<const int4 *>(c.recs + h));
+                    head = ld_state<SPLIT>(reinterpret_cast<const int4 *>(rec_ptr<SPLIT>(c, h)));
                     keep = head.x >= x0 - 64 && head.x < x1 + 64 && head.y >= y0 - 64 && head.y < y1 + 64;
                 }
                 const uint32_t kb = __ballot_sync(MPP_FULL, keep);
@@ -1309,7 +1309,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     // phase C: one thread per object loads its full record
     for (int p = sidx; p < n0; p += sg) {
         const uint32_t h = w.order[p];
-        const Rec<R> rec = load_rec(c.recs + h);
+        const Rec<R> rec = load_rec_state<SPLIT>(rec_ptr<SPLIT>(c, h));
         const bool inw = rec.x >= x0 && rec.x < x1 && rec.y >= y0 && rec.y < y1;
         const bool inner = rec.x >= x0 - 32 && rec.x < x1 + 32 && rec.y >= y0 - 32 && rec.y < y1 + 32;
         w.x[p] = rec.x; w.y[p] = rec.y; w.cls[p] = rec.cls; w.handle[p] = h; w.uid[p] = rec.uid;
@@ -1404,7 +1404,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             if (w.n >= W2_K) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
             else {
                 fill_pairs(m, w, -1, true, g.a, lane, sx, sy, po, pa);
-                commit_proposal(c, w, g, first, lane, sx, sy, po, pa);
+                commit_proposal<R, SPLIT>(c, w, g, first, lane, sx, sy, po, pa);
             }
         }
         __syncthreads();
@@ -1459,7 +1459,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
                 if (!e.has_add && e.r >= 0) w.n_death += 1;
             }
             if (w.n >= W2_K && e.has_add && e.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
-            else commit_proposal(c, w, e, mine, lane, sx, sy, po, pa);
+            else commit_proposal<R, SPLIT>(c, w, e, mine, lane, sx, sy, po, pa);
         }
         __syncthreads();
 #ifdef MPP_TRACE
@@ -1485,8 +1485,9 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
     if (threadIdx.x == 0) {
         if (w.masks_dirty) {
-            __threadfence();  // records before masks: a window staging these cells must never see a mask bit without its record
-            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(c.mask + w.ccell[q], w.cmask[q]);
+            // records before masks: a window staging these cells must never see a mask bit without its record
+            if (SPLIT) __threadfence_system(); else __threadfence();
+            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
         }
         atomicAdd(c.counters + 0, (unsigned long long)w.n_done);
         atomicAdd(c.counters + 1, (unsigned long long)w.n_acc);

@@ -243,6 +243,16 @@ class Engine:
                                          float(det_sum) if det_sum is not None else -1.0))
         self.launches += 2
 
+    def set_maps_band(self, det_band, marks_band, row0: int, det_sum_scene: float):
+        """Band-local maps of a split scene (mpp_set_maps_band): det_band (rows, W), marks_band (3, rows, W, 32) = the scene rows
+        [row0, row0 + rows); det_sum_scene = sum of the whole detection map."""
+        self._det = self._dev(det_band, torch.float32)
+        self._marks = self._dev(marks_band, torch.float32)
+        rows = int(self._det.shape[0])
+        assert tuple(self._det.shape) == (rows, self.shape[1]) and tuple(self._marks.shape) == (3, rows, self.shape[1], 32)
+        _lib.check(self.lib.mpp_set_maps_band(self.ctx, self._det.data_ptr(), self._marks.data_ptr(), int(row0), rows, float(det_sum_scene)))
+        self.launches += 5
+
     def set_model(self, model: ModelSpec):
         self.model = model
         p = model.to_c()
@@ -375,6 +385,24 @@ class Engine:
             return out, float(dbg.cpu().item())
         return out
 
+    # ------------------------------------------------------------------------------------------ scene split across GPUs
+    def split_export(self) -> bytes:
+        """CUDA IPC handles of this context's occupancy masks, records and completion grid (mpp_split_export)."""
+        buf = C.create_string_buffer(3 * _lib.IPC_HANDLE_BYTES)
+        _lib.check(self.lib.mpp_split_export(self.ctx, buf))
+        return buf.raw
+
+    def split_attach(self, row_lo: int, row_hi: int, up_handles: Optional[bytes], down_handles: Optional[bytes]):
+        """This context samples the band [row_lo, row_hi) of its scene; the neighbour bands live in other processes."""
+        _lib.check(self.lib.mpp_split_attach(self.ctx, int(row_lo), int(row_hi), up_handles, down_handles))
+
+    def split_attach_local(self, row_lo: int, row_hi: int, up: Optional["Engine"], down: Optional["Engine"]):
+        _lib.check(self.lib.mpp_split_attach_local(self.ctx, int(row_lo), int(row_hi), None if up is None else up.ctx,
+                                                   None if down is None else down.ctx))
+
+    def split_detach(self):
+        _lib.check(self.lib.mpp_split_detach(self.ctx))
+
     def window_stats(self) -> dict:
         """Per-kernel tallies of the window sampler since the last call (mpp_window_stats; reads and resets)."""
         raw = (C.c_ulonglong * _lib.WINDOW_STATS)()
@@ -500,3 +528,27 @@ class Engine:
     def unpack_rows(self, row_lo: int, row_hi: int, records: torch.Tensor):
         rec = records.to(device=self.device, dtype=torch.float64).contiguous()
         _lib.check(self.lib.mpp_unpack_rows(self.ctx, int(row_lo), int(row_hi), rec.data_ptr() if len(rec) else None, len(rec)))
+
+
+def run_windows_batch(engines: Sequence[Engine], seeds: Sequence[int], n_sweeps: int, proposals_per_visit: int = 96, n_warps: int = 8,
+                      t0: float = 1.0, alpha_t: float = 1.0, t_target: float = 0.0, grid_seed: Optional[int] = None, sweep_offset: int = 0,
+                      max_ctas: int = 0, read_counters: bool = True, debug: bool = False):
+    """mpp_run_windows_batch: the window sampler over a batch of scenes of equal shape (or over this rank's band of a split
+    scene: one engine) in ONE persistent launch on the first engine's stream.  Returns the summed counters
+    [proposals, accepted, births, deaths, evaluated, 0, 0, 0] (and the largest |fast - brute-force Delta E| with debug=True)."""
+    engines = list(engines)
+    n = len(engines)
+    lib = engines[0].lib
+    ctxs = (C.c_void_p * n)(*[e.ctx for e in engines])
+    sd = (C.c_uint64 * n)(*[int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds])
+    cnt = (C.c_ulonglong * 8)()
+    dbg = torch.zeros(1, dtype=torch.float32, device=engines[0].device) if debug else None
+    gs = int(seeds[0] if grid_seed is None else grid_seed) & 0xFFFFFFFFFFFFFFFF
+    _lib.check(lib.mpp_run_windows_batch(ctxs, sd, n, gs, int(n_sweeps), int(proposals_per_visit), int(n_warps), float(t0), float(alpha_t),
+                                         float(t_target), int(sweep_offset), int(max_ctas), cnt if read_counters else None,
+                                         None if dbg is None else dbg.data_ptr()))
+    engines[0].launches += 1 if n_sweeps > 0 else 0
+    out = [int(v) for v in cnt] if read_counters else None
+    if debug:
+        return out, float(dbg.cpu().item())
+    return out

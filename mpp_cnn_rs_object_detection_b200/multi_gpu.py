@@ -1,6 +1,12 @@
 """Host-side sharding of the sampler across the GPUs of one box (one process per GPU, torch.distributed).
 
-Two decompositions:
+Decompositions:
+
+* one scene split into row bands with PEER ACCESS (`PeerSplitScene`, the production path of BASELINE configs[3]): every rank
+  runs ONE persistent dataflow kernel over the windows of its band (mpp_run_windows_batch); the boundary cells of the
+  neighbour bands are read and written directly in the neighbours' device memory over NVLink (CUDA IPC mappings) and window
+  completions are stamped into the neighbours' completion grids, so there is no exchange step, no host synchronisation and no
+  collective on the data path.  torch.distributed only carries the 192-byte IPC handles at set-up;
 
 * independent tiles / images (`shard_items`): each rank samples its own images; no data-path collective, results are
   gathered on the host (the reference's own decomposition: mpp_model.py:231-264 maps patches over a process pool);
@@ -147,6 +153,71 @@ class SplitScene:
         if from_down is not None:
             n = int(from_down[0, 0].item())
             self.engine.unpack_rows(g_down, self.r1 + HALO + BAND_ALIGN, from_down[1:1 + n])
+
+
+class PeerSplitScene:
+    """One rank's band of a scene sampled with peer access to the neighbour bands (see the module docstring).  `engine` is an
+    Engine of the WHOLE scene's shape; its maps may be band-local (Engine.set_maps_band over `map_rows()`)."""
+
+    MIN_BAND = 384
+    MAP_MARGIN = 64   # map rows a rank needs beyond its band: a window starting in the band reaches 31 rows below it, a
+                      # data-driven translation 8 more
+
+    def __init__(self, engine, height: int, rank: int, world: int):
+        self.engine, self.height, self.rank, self.world = engine, int(height), int(rank), int(world)
+        bands = row_bands(height, world)
+        if world > 1 and min(b[1] - b[0] for b in bands) < self.MIN_BAND:
+            raise ValueError(f"{height} rows split {world} ways gives bands under {self.MIN_BAND} rows")
+        self.r0, self.r1 = bands[rank]
+        self.attached = False
+
+    @staticmethod
+    def map_rows(height: int, rank: int, world: int) -> Tuple[int, int]:
+        r0, r1 = row_bands(height, world)[rank]
+        return max(0, r0 - PeerSplitScene.MAP_MARGIN), min(height, r1 + PeerSplitScene.MAP_MARGIN)
+
+    def select_initial(self, xy: np.ndarray) -> np.ndarray:
+        """Objects this rank stores: those whose 32-px cell row lies in its band (bands are whole cell rows)."""
+        return (xy[:, 0] >= self.r0) & (xy[:, 0] < self.r1)
+
+    def attach_dist(self, group=None):
+        """Exchanges the CUDA IPC handles of the contexts with the two neighbour ranks and maps their state (host plumbing over
+        torch.distributed; ends with a barrier: nobody may run before everybody is attached)."""
+        import torch.distributed as dist
+        mine = self.engine.split_export()
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+        else:
+            handles = [mine]
+        up = handles[self.rank - 1] if self.rank > 0 else None
+        down = handles[self.rank + 1] if self.rank < self.world - 1 else None
+        self.engine.split_attach(self.r0, self.r1, up, down)
+        self.attached = True
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def attach_local(self, up_engine, down_engine):
+        self.engine.split_attach_local(self.r0, self.r1, up_engine, down_engine)
+        self.attached = True
+
+    def run(self, n_sweeps: int, per_visit: int, n_warps: int, t0: float, seed: int, alpha_t: float = 1.0, t_target: float = 0.0,
+            sweep_offset: int = 0, max_ctas: int = 0, read_counters: bool = False):
+        """`n_sweeps` sweeps of this rank's band: one asynchronous launch.  Every rank must issue the same calls."""
+        from .engine import run_windows_batch
+        assert self.attached, "attach_dist() / attach_local() first"
+        return run_windows_batch([self.engine], [seed], n_sweeps, per_visit, n_warps=n_warps, t0=t0, alpha_t=alpha_t, t_target=t_target,
+                                 sweep_offset=sweep_offset, max_ctas=max_ctas, read_counters=read_counters)
+
+    def owned_objects(self):
+        """(xy, marks, uid) of this rank's band."""
+        _, xy, marks, uid = self.engine.read_objects()
+        return xy, marks, uid
+
+    def detach(self):
+        if self.attached:
+            self.engine.split_detach()
+            self.attached = False
 
 
 # ------------------------------------------------------------------------------------------------ transports

@@ -178,3 +178,80 @@ def make_scene_torch(seed: int, shape: Tuple[int, int], n_rect: int, device, blo
             win /= win.sum(-1, keepdim=True)
             flat[pix] = win
     return objs, det, marks
+
+
+BAND_BLOCK = 64  # rows per independently seeded block of the mark-map background (band generator)
+
+
+def det_map_numpy(objs: np.ndarray, shape: Tuple[int, int], blob_sigma: float = 2.0) -> np.ndarray:
+    """Detection map of a scene with a FIXED accumulation order (np.add.at), so that every rank of a split scene holds bit-equal
+    copies of the rows it shares with its neighbours (the atomics of the torch builder may round overlapping blobs differently)."""
+    h, w = shape
+    det = np.full(h * w, 0.02, dtype=np.float32)
+    r = int(math.ceil(3 * blob_sigma))
+    ax = np.arange(-r, r + 1)
+    dx, dy = np.meshgrid(ax, ax, indexing="ij")
+    blob = (0.97 * np.exp(-(dx ** 2 + dy ** 2).astype(np.float32) / np.float32(2 * blob_sigma ** 2))).astype(np.float32).reshape(1, -1)
+    if len(objs):
+        px = objs[:, 0].astype(np.int64)[:, None] + dx.reshape(1, -1)
+        py = objs[:, 1].astype(np.int64)[:, None] + dy.reshape(1, -1)
+        ok = (px >= 0) & (px < h) & (py >= 0) & (py < w)
+        np.add.at(det, (px * w + py)[ok], np.broadcast_to(blob, px.shape)[ok])
+    return np.clip(det, 0.0, 0.999).astype(np.float32).reshape(h, w)
+
+
+def make_scene_band_torch(seed: int, shape: Tuple[int, int], n_rect: int, device, row0: int = 0, rows: int = None,
+                          peak: float = 0.8, peak_radius: int = 4, objs: np.ndarray = None, det: np.ndarray = None):
+    """The rows [row0, row0 + rows) of a scene whose maps are a function of (seed, pixel) only, whatever the band: the mark-map
+    background comes from one generator per 64-row block and the peaked windows are assigned pixel by pixel to the
+    lowest-numbered object within reach (order-independent), so ranks that hold overlapping bands of one scene hold
+    bit-equal rows.  Returns (objects of the WHOLE scene (N,5) f64, det of the whole scene (H,W) f32 numpy,
+    marks of the band (3, rows, W, 32) on `device`)."""
+    import torch
+
+    h, w = shape
+    rows = h - row0 if rows is None else rows
+    if objs is None:
+        objs = make_objects(seed, shape, n_rect)
+    if det is None:
+        det = det_map_numpy(objs, shape)
+    n = len(objs)
+    cls = torch.as_tensor(mark_classes(objs), device=device)
+    marks = torch.empty((3, rows, w, N_CLASSES), dtype=torch.float32, device=device)
+    gen = torch.Generator(device=device)
+    # lowest-numbered object whose (2 r + 1)^2 window covers each pixel of the band
+    owner = torch.full((rows * w,), n, dtype=torch.int64, device=device)
+    if n > 0:
+        near = np.nonzero((objs[:, 0] >= row0 - peak_radius) & (objs[:, 0] < row0 + rows + peak_radius))[0]
+        if len(near):
+            idx = torch.as_tensor(near, device=device)
+            cx = torch.as_tensor(objs[near, 0].astype(np.int64), device=device)
+            cy = torch.as_tensor(objs[near, 1].astype(np.int64), device=device)
+            ax = torch.arange(-peak_radius, peak_radius + 1, device=device)
+            dx, dy = torch.meshgrid(ax, ax, indexing="ij")
+            px = cx[:, None] + dx.reshape(1, -1) - row0
+            py = cy[:, None] + dy.reshape(1, -1)
+            ok = (px >= 0) & (px < rows) & (py >= 0) & (py < w)
+            owner.scatter_reduce_(0, (px * w + py)[ok], idx[:, None].expand(-1, px.shape[1])[ok], reduce="amin")
+    has = owner < n
+    pix = torch.nonzero(has).squeeze(1)
+    for i in range(3):
+        m = marks[i]
+        b0, b1 = row0 // BAND_BLOCK, (row0 + rows + BAND_BLOCK - 1) // BAND_BLOCK
+        for b in range(b0, b1):
+            gen.manual_seed((seed * 1000003 + i * 7919 + b * 104729 + 12345) & 0x7FFFFFFFFFFF)
+            blk = torch.rand((BAND_BLOCK, w, N_CLASSES), generator=gen, device=device, dtype=torch.float32)
+            blk = blk * blk + 1e-3
+            blk /= blk.sum(-1, keepdim=True)
+            s0, s1 = max(b * BAND_BLOCK, row0), min((b + 1) * BAND_BLOCK, row0 + rows, h)
+            m[s0 - row0:s1 - row0] = blk[s0 - b * BAND_BLOCK:s1 - b * BAND_BLOCK]
+        if len(pix):
+            c = cls[owner[pix], i]
+            flat = m.view(-1, N_CLASSES)
+            win = flat[pix]
+            rest = 1.0 - win.gather(1, c[:, None]).squeeze(1)
+            win *= ((1.0 - peak) / rest.clamp_min(1e-6))[:, None]
+            win.scatter_(1, c[:, None], peak)
+            win /= win.sum(-1, keepdim=True)
+            flat[pix] = win
+    return objs, det, marks

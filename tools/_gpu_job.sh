@@ -1,6 +1,4 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_window_trace.py -x -q 2>&1 | tail -15 > gpurun_out/trace_test.log
-( time timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r2_b.json 2> gpurun_out/bench_r2_b.err ) 2>> gpurun_out/trace_test.log
-( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_ref.json 2> gpurun_out/bench_r2_ref.err ) 2>> gpurun_out/trace_test.log
-free -g >> gpurun_out/trace_test.log
+N=$1
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_r2_n$N.json 2> gpurun_out/bench_r2_n$N.err ) 2> gpurun_out/bench_r2_n$N.time
 echo done
