@@ -77,6 +77,9 @@ def parse_args():
     ap.add_argument("--split-size", type=int, default=8192, help="side of the scene of the split-scene record (BASELINE configs[3])")
     ap.add_argument("--split-n-rect", type=int, default=0, help="candidate rectangles of that scene (0: 33000 per 8192^2 -> ~30k objects)")
     ap.add_argument("--no-split", action="store_true", help="skip the split-scene sub-record")
+    ap.add_argument("--tiles", type=int, default=256, help="tiles of the tile-batch sub-record (BASELINE configs[4])")
+    ap.add_argument("--tile-size", type=int, default=512)
+    ap.add_argument("--no-tiles", action="store_true", help="skip the tile-batch sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single-chain", action="store_true", help="skip the whole-scene single-chain CPU leg")
@@ -382,6 +385,96 @@ def split_record(args, world, rank, device, dist):
     return rec
 
 
+def tiles_record(args, world, rank, device, dist):
+    """BASELINE configs[4]: a batch of independent 512x512 tiles sharded over the ranks (multi_gpu.shard_items), the position and
+    shape U-Nets (PyTorch/cuDNN, random initialisation: no checkpoints travel) producing the detection and mark maps ON THE DEVICE,
+    the sampler reading them in place (no host round trip, no .npy detour), all tiles of a rank in ONE persistent dataflow launch
+    (api.sample_rjmcmc_tiles -> mpp_run_windows_batch).  Randomly initialised networks detect nothing, so a synthetic scene
+    (make_synth recipe, ~160 vehicles per tile) is written into their output maps on the device before the sampler reads them.
+    Timed per step, host wall clock with device synchronisation at the stage boundaries, max over ranks: U-Nets, set-up
+    (prefix sums, naive initial configuration), sampling, read-back."""
+    import torch
+
+    import mpp_cnn_rs_object_detection_b200.api as api
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg, synth
+    from mpp_cnn_rs_object_detection_b200.map_producers import MapProducer
+
+    n_tiles, side = args.tiles, args.tile_size
+    mine = mg.shard_items(n_tiles, world, rank)
+    n_rect = int(round(2600 * side * side / (2048.0 * 2048.0)))
+    objs_per_tile = [synth.make_objects(args.seed + 1000 + k, (side, side), n_rect) for k in mine]
+    torch.manual_seed(1234)
+    producer = MapProducer().to(device).eval()
+    images = synth.render_tiles_torch(objs_per_tile, (side, side), device, seed=args.seed + rank)
+    setup = api.LegacyEnergySetup(calibration_params={}, energy_calibration=api.LegacyEnergiesCalibration(
+        CALIB_HRCM["detection_threshold"], list(CALIB_HRCM["coefs"]), list(CALIB_HRCM["intercepts"]), CALIB_HRCM["min_area"], CALIB_HRCM["max_area"]))
+    comb = api.HierarchicalEnergyCombinator(np.array(HRC["weights_data"]), np.array(HRC["weights_prior"]), np.array(HRC["data_prior_weights"]),
+                                            HRC["detection_threshold"], HRC["bias"])
+    ncell = ((side + 31) // 32) ** 2
+    budget = args.sweeps * ncell * args.per_visit
+    params = dict(num_samples=1, energy_combinator=comb, init_config="naive", init_temperature=args.temperature, alpha_t=1.0, burn_in=budget - 3,
+                  energy_setup=setup, samples_interval=1, target_temperature=0.0, proposals_per_visit=args.per_visit, warps_per_window=args.warps,
+                  reuse_device_maps=False)
+    rng = np.random.default_rng(args.seed + 300 + rank)
+    chunk = 16  # tiles per U-Net forward pass
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        t0 = time.perf_counter()
+        dets, markss = [], []
+        for s0 in range(0, len(mine), chunk):
+            d, m = producer.produce(images[s0:s0 + chunk])
+            synth.inject_objects_torch(d, m, objs_per_tile[s0:s0 + chunk])
+            dets.append(d); markss.append(m)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        tiles = []
+        for j, d in enumerate(dets):
+            for q in range(d.shape[0]):
+                tiles.append(api.ImageWMaps(name=f"tile_{rank}_{j * chunk + q}", shape=(side, side), image=None, detection_map=d[q],
+                                            param_dist_maps=[markss[j][q, 0], markss[j][q, 1], markss[j][q, 2]], mappings=api.default_mappings(),
+                                            param_names=["size", "ratio", "angle"]))
+        res, st = api.sample_rjmcmc_tiles(tiles, rng, return_stats=True, **params)
+        t2 = time.perf_counter()
+        return {"unet_s": t1 - t0, "setup_s": st["setup_s"], "sample_s": st["sample_s"], "collect_s": st["collect_s"], "total_s": t2 - t0,
+                "evaluated": st["evaluated"], "objects": sum(len(r) for r in res), "launches": st["sampler_launches"]}
+
+    steps, warm = max(2, min(args.steps, 3)), 1
+    for _ in range(warm):
+        step()
+    barrier()
+    torch.cuda.synchronize()
+    acc = None
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        r = step()
+        acc = r if acc is None else {k: acc[k] + v for k, v in r.items()}
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t_all
+    v = torch.tensor([t_all, acc["unet_s"], acc["setup_s"], acc["sample_s"], acc["collect_s"]], dtype=torch.float64, device=device)
+    tot = torch.tensor([float(acc["evaluated"]), float(acc["objects"]), float(acc["launches"])], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    t_all, t_unet, t_setup, t_sample, t_collect = (float(x) for x in v.tolist())
+    evaluated, objects, launches = (float(x) for x in tot.tolist())
+    rec = {"workload": f"{n_tiles} synthetic {side}x{side} tiles (independent chains), ~{n_rect} candidate rectangles each, hrcM energies, fixed T={args.temperature}, "
+                       f"maps produced on the device by randomly initialised position / shape U-Nets with the synthetic scene written into them",
+           "n_gpus": world, "tiles": n_tiles, "tiles_per_rank": len(mine), "steps": steps, "scaling": "strong (the batch is fixed, tiles are sharded)",
+           "tiles_per_s": n_tiles * steps / t_all, "value": evaluated / t_all, "unit": UNIT, "ms_per_batch": 1e3 * t_all / steps,
+           "sampler_value": evaluated / t_sample, "sampler_value_note": "proposals/s over the sampling stage alone (one mpp_run_windows_batch launch per rank and step)",
+           "stage_s_per_batch": {"unets": t_unet / steps, "setup": t_setup / steps, "sampling": t_sample / steps, "read_back": t_collect / steps},
+           "unet_share": t_unet / t_all, "proposals_per_tile": evaluated / (n_tiles * steps), "objects_found_per_tile": objects / (n_tiles * steps),
+           "sampler_launches_per_step_per_rank": launches / steps / world, "h2d_bytes_per_step": 0,
+           "call": "map_producers.MapProducer.produce(images on device) -> api.sample_rjmcmc_tiles(ImageWMaps with DEVICE maps, init_config='naive')"}
+    del producer, images
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_split(args):
     """`bench.py --split`: the split-scene record alone, as the bench line (BASELINE configs[3])."""
     import torch
@@ -626,6 +719,8 @@ def run_b200(args):
     torch.cuda.empty_cache()
     if not args.no_split and args.sampler == "windows":
         line["split"] = split_record(args, world, rank, device, dist)
+    if not args.no_tiles and args.sampler == "windows":
+        line["tiles"] = tiles_record(args, world, rank, device, dist)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -52,11 +52,24 @@ def _evict(key):
     _MAPS_CACHE.pop(key, None)
 
 
+def _array_key(a):
+    """Cache key of one source array: where its data lives, its shape / dtype, and something that changes when it is edited in
+    place -- the version counter of a tensor, a strided sample of a numpy array (about 1e4 elements; a cheap fingerprint, not a
+    proof: callers that rewrite their maps in place should pass reuse_device_maps=False)."""
+    if isinstance(a, torch.Tensor):
+        return ("t", a.data_ptr(), tuple(a.shape), str(a.dtype), a._version)
+    arr = np.asarray(a)
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 8191)
+    return ("n", arr.__array_interface__["data"][0], arr.shape, str(arr.dtype), float(np.sum(flat[::step], dtype=np.float64)))
+
+
 def device_maps(det, marks: Sequence, device=None, reuse: bool = True) -> DeviceMaps:
     """Uploads the maps to the device (once per set of source arrays when reuse=True).  Tensors already on the device are
     used in place; pinned host tensors are copied asynchronously on the current stream."""
     stacked = isinstance(marks, torch.Tensor) and marks.dim() == 4
-    key = (id(det), id(marks)) if stacked else (id(det),) + tuple(id(m) for m in marks)
+    sources = [det, marks] if stacked else [det] + list(marks)
+    key = tuple(_array_key(a) for a in sources) if reuse else None
     hit = _MAPS_CACHE.get(key) if reuse else None
     if hit is not None:
         return hit
@@ -111,12 +124,13 @@ def device_maps(det, marks: Sequence, device=None, reuse: bool = True) -> Device
     if not reuse:
         return out
     _MAPS_CACHE[key] = out
-    try:
-        weakref.finalize(det, _evict, key)
-    except TypeError:
-        pass
-    if len(_MAPS_CACHE) > 8:  # bound the cache: drop the oldest entries
-        for k in list(_MAPS_CACHE.keys())[:-8]:
+    for a in sources:  # the entry dies with ANY of its source arrays (an address can be handed out again)
+        try:
+            weakref.finalize(a, _evict, key)
+        except TypeError:
+            pass
+    if len(_MAPS_CACHE) > 2:  # bound the cache (a 2048^2 map set is 1.6 GB): drop the oldest entries
+        for k in list(_MAPS_CACHE.keys())[:-2]:
             _MAPS_CACHE.pop(k, None)
     return out
 
@@ -277,9 +291,13 @@ class DeviceState:
 
     # -- model
     def use_combinator(self, combinator):
-        key = None if combinator is None else id(combinator)
+        # keyed on the VALUES sent to the device: a combinator whose weights are edited in place (training / tuning loops) is
+        # sent again
+        spec = apply_combinator(self.layout, combinator)
+        key = None if combinator is None else (type(combinator).__name__, spec.combinator, tuple(float(v) for v in spec.comb_w),
+                                                float(spec.comb_bias), float(spec.comb_threshold))
         if key != self._comb_key:
-            self.engine.set_model(apply_combinator(self.layout, combinator))
+            self.engine.set_model(spec)
             self._comb_key = key
 
     def rebind_layout(self, layout: TermLayout):

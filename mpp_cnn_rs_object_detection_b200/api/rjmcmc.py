@@ -371,15 +371,24 @@ def sample_rjmcmc_batch(images, rng: np.random.Generator, with_scores: bool = Fa
     return results
 
 
-def sample_rjmcmc_tiles(images, rng: np.random.Generator, n_streams: int = 8, **params):
-    """Independent chains on a batch of small tiles (BASELINE configs[4]: e.g. 256 tiles of 512x512), run concurrently on
-    `n_streams` CUDA streams so that their persistent kernels share the SMs (one 512^2 tile exposes only ~36 concurrently
-    active windows, far fewer than the GPU can hold).  Single-sample, parallel sampler only.  `params` as sample_rjmcmc
-    (init_config 'naive' / 'gt' / list / None).  Returns one list of Rectangle per tile."""
+def sample_rjmcmc_tiles(images, rng: np.random.Generator, return_stats: bool = False, n_streams: int = None, **params):
+    """Independent chains on a batch of small tiles (BASELINE configs[4]: e.g. 256 tiles of 512x512; the reference maps such
+    patches over a process pool, mpp_model.py:231-264).  All tiles of one shape are sampled by ONE persistent dataflow launch
+    (mpp_run_windows_batch): one 512^2 tile exposes only ~36 concurrently active windows, a batch fills the GPU like one large
+    scene.  The maps of a tile may be device tensors (e.g. straight from map_producers.MapProducer): they are used in place.
+    Single-sample, parallel sampler only; `params` as sample_rjmcmc (init_config 'naive' / 'gt' / list / None).  Returns one list
+    of Rectangle per tile (and, with return_stats=True, a dict of counters and stage times).  `n_streams` is accepted for
+    compatibility with the first-generation implementation (one stream and one launch per tile) and ignored."""
     import torch
+
+    from ..engine import run_windows_batch
     images = list(images)
     if params.get("num_samples", 1) != 1 or params.get("sampler", "parallel") != "parallel":
         raise ValueError("sample_rjmcmc_tiles runs one parallel-sampler chain per tile (num_samples=1)")
+    if params.get("use_split_merge"):
+        raise NotImplementedError("the optional split / merge kernels run through the step-by-step chain (sample_rjmcmc(sampler='sequential'))")
+    if params.get("precision", "fp32") != "fp32":
+        raise NotImplementedError("the window sampler is float32 only")
     energy_setup, comb = params["energy_setup"], params["energy_combinator"]
     init_config = params.get("init_config", "naive")
     burn_in, interval = params["burn_in"], params["samples_interval"]
@@ -391,41 +400,50 @@ def sample_rjmcmc_tiles(images, rng: np.random.Generator, n_streams: int = 8, **
         alpha_t, t_target = np.power(t_target / t0, 1 / burn_in), 0
     pv, nw = int(params.get("proposals_per_visit", 96)), int(params.get("warps_per_window", 8))
     max_iter = int(burn_in) + 2 * int(interval)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(n_streams, len(images))))]
-    main = torch.cuda.current_stream(dev)
+    t_start = time.perf_counter()
     states = []
-    for i, img in enumerate(images):  # phase 1: upload, index, initial configuration (each tile on its stream)
-        s = streams[i % len(streams)]
-        s.wait_stream(main)
-        with torch.cuda.stream(s):
-            unit, pair = energy_setup.make_energies(img)
-            pts = EPointsSet([], img.shape, unit, pair, reuse_device_maps=params.get("reuse_device_maps", True))
-            st = pts._state
-            if isinstance(init_config, str) and init_config == "gt":
-                st.add_many(img.gt_config)
-            elif isinstance(init_config, str) and init_config == "naive":
-                st.engine.naive_init(float(energy_setup.detection_threshold), 6.0)
-            elif init_config is not None:
-                st.add_many(list(init_config))
-            n0 = len(st.engine)
-            st.use_kernels(max(1, n0), kernel_probabilities_default())
-            st.use_combinator(comb)
-            states.append((pts, s))
+    for img in images:  # phase 1: index the maps, initial configuration
+        unit, pair = energy_setup.make_energies(img)
+        pts = EPointsSet([], img.shape, unit, pair, reuse_device_maps=params.get("reuse_device_maps", True))
+        st = pts._state
+        if isinstance(init_config, str) and init_config == "gt":
+            st.add_many(img.gt_config)
+        elif isinstance(init_config, str) and init_config == "naive":
+            st.engine.naive_init(float(energy_setup.detection_threshold), 6.0)
+        elif init_config is not None:
+            st.add_many(list(init_config))
+        n0 = len(st.engine)
+        st.use_kernels(max(1, n0), kernel_probabilities_default())
+        st.use_combinator(comb)
+        states.append(pts)
+    t_setup = time.perf_counter()
     seeds = [int(rng.integers(0, 2 ** 62)) for _ in images]
-    for (pts, s), img, seed in zip(states, images, seeds):  # phase 2: every chain is launched before any result is read
-        ncell = ((img.shape[0] + 31) // 32) * ((img.shape[1] + 31) // 32)
-        per_sweep = ncell * pv
-        with torch.cuda.stream(s):
-            pts._state.engine.run_windows(-(-(max_iter + 1) // per_sweep), pv, nw, t0=float(t0), alpha_t=float(np.power(alpha_t, per_sweep)),
-                                          t_target=float(t_target), seed=seed, read_counters=False)
+    by_shape = {}
+    for k, img in enumerate(images):
+        by_shape.setdefault(tuple(img.shape[:2]), []).append(k)
+    totals = np.zeros(8, dtype=np.int64)
+    n_launches = 0
+    for shape, idx in by_shape.items():  # phase 2: one launch per shape
+        per_sweep = ((shape[0] + 31) // 32) * ((shape[1] + 31) // 32) * pv
+        n_sweeps = -(-(max_iter + 1) // per_sweep)
+        cnt = run_windows_batch([states[k]._state.engine for k in idx], [seeds[k] for k in idx], n_sweeps, pv, n_warps=nw, t0=float(t0),
+                                alpha_t=float(np.power(alpha_t, per_sweep)), t_target=float(t_target), grid_seed=seeds[idx[0]],
+                                read_counters=return_stats)
+        n_launches += 1
+        if cnt is not None:
+            totals += np.array(cnt, dtype=np.int64)
+    if return_stats:
+        torch.cuda.synchronize()
+    t_sample = time.perf_counter()
     out = []
-    for pts, s in states:  # phase 3: collect
-        with torch.cuda.stream(s):
-            pts._state.refresh_from_device()
-            out.append(list(pts._state.objects()))
-    for s in streams:
-        main.wait_stream(s)
+    for pts in states:  # phase 3: collect
+        pts._state.refresh_from_device()
+        out.append(list(pts._state.objects()))
+    t_end = time.perf_counter()
+    if return_stats:
+        return out, {"proposals": int(totals[0]), "accepted": int(totals[1]), "births": int(totals[2]), "deaths": int(totals[3]),
+                     "evaluated": int(totals[4]), "sampler_launches": n_launches, "setup_s": t_setup - t_start,
+                     "sample_s": t_sample - t_setup, "collect_s": t_end - t_sample}
     return out
 
 

@@ -1299,6 +1299,7 @@ int mpp_sample_births(mpp_ctx *h, int n, uint64_t seed, int32_t *out) {
 
 int mpp_naive_init(mpp_ctx *h, double detection_threshold, double nms_distance, int *n_host) {
     NEED(h, h->maps_set && h->model_set, "mpp_naive_init: set maps and model first");
+    if (h->map_rows != h->H) return fail(MPP_ERR_STATE, "mpp_naive_init: needs the maps of the whole scene (band-local maps are set)");
     if (nms_distance < 0 || nms_distance > 32) return fail(MPP_ERR_INVALID, "mpp_naive_init: nms_distance in [0,32]");
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = h->H * h->W;
@@ -1307,10 +1308,13 @@ int mpp_naive_init(mpp_ctx *h, double detection_threshold, double nms_distance, 
     const int blocks = (n + 255) / 256;
     int *flags = reinterpret_cast<int *>(h->d_counters);  // reuse: 2 ints
     k_nms_threshold<<<blocks, 256, 0, h->stream>>>(h->det, n, (float)detection_threshold, h->d_nms_state);
+    // rounds of select / suppress are idempotent once nothing remains undecided, so they are issued six at a time and the host
+    // only looks at the flags of the last one (one synchronisation per call on typical maps instead of one per round)
     for (int round = 0; round < 4096; ++round) {
         CUDA_TRY(cudaMemsetAsync(flags, 0, 2 * sizeof(int), h->stream));
-        k_nms_select<<<blocks, 256, 0, h->stream>>>(h->det, h->H, h->W, rad, rad2, h->d_nms_state, flags);
+        k_nms_select<<<blocks, 256, 0, h->stream>>>(h->det - (ptrdiff_t)h->map_row0 * h->W, h->H, h->W, rad, rad2, h->d_nms_state, flags);
         k_nms_suppress<<<blocks, 256, 0, h->stream>>>(h->H, h->W, rad, rad2, h->d_nms_state, flags + 1);
+        if (round % 6 != 5) continue;
         CUDA_TRY(cudaMemcpyAsync(h->h_pinned, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (!h->h_pinned[1]) break;

@@ -166,7 +166,14 @@ class Engine:
     """One mpp_ctx.  Not thread-safe; bound to one CUDA device and the current torch stream at creation."""
 
     _POOL: dict = {}      # (device index, H, W, precision) -> idle contexts (device allocations kept)
-    POOL_SIZE = 4
+    POOL_BYTES = 4 << 30  # idle contexts kept per key: up to this many bytes of device allocations, at least 4, at most 1024 contexts
+                          # (a batch of 256 tiles of 512^2 re-uses its 256 contexts: creating and destroying one costs ~25 cudaMalloc / cudaFree)
+
+    @staticmethod
+    def _pool_size(shape) -> int:
+        h, w = shape
+        per_ctx = (h // 32 + 1) * (w // 32 + 1) * (32 * 64 + 16) + h * (w + 1) * 8 + 3 * h * w * 4 + h * w  # records, row prefix sums, class sums, NMS scratch
+        return int(max(4, min(1024, Engine.POOL_BYTES // max(1, per_ctx))))
 
     def __init__(self, shape: Tuple[int, int], device: Optional[torch.device] = None, precision: str = "fp32"):
         self.lib = _lib.load()
@@ -201,7 +208,7 @@ class Engine:
             self.ctx = None
             self._det = self._marks = None
             idle = Engine._POOL.setdefault(self._key, [])
-            if len(idle) < Engine.POOL_SIZE:
+            if len(idle) < Engine._pool_size(self.shape):
                 idle.append(ctx)
             else:
                 self.lib.mpp_ctx_destroy(ctx)

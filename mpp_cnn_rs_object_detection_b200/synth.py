@@ -255,3 +255,63 @@ def make_scene_band_torch(seed: int, shape: Tuple[int, int], n_rect: int, device
             win /= win.sum(-1, keepdim=True)
             flat[pix] = win
     return objs, det, marks
+
+
+def render_tiles_torch(objs_per_tile, shape: Tuple[int, int], device, seed: int = 0):
+    """Synthetic RGB tiles (B, 3, H, W) in [0, 1]: noise background + a bright blob per object (what data/make_synth_data.py
+    renders as filled rectangles); the input of the map-producing CNNs in the tile benchmark."""
+    import torch
+
+    h, w = shape
+    b = len(objs_per_tile)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 77)
+    img = 0.2 * torch.rand((b, 3, h, w), generator=gen, device=device, dtype=torch.float32)
+    for k, objs in enumerate(objs_per_tile):
+        if len(objs):
+            det = torch.as_tensor(det_map_numpy(objs, shape, blob_sigma=3.0), device=device)
+            img[k] += 0.8 * det.unsqueeze(0)
+    return img.clamp_(0.0, 1.0)
+
+
+def inject_objects_torch(det, marks, objs_per_tile, peak: float = 0.8, peak_radius: int = 4, blob_sigma: float = 2.0):
+    """Writes a synthetic scene into CNN-produced maps, on the device and in place: randomly initialised networks detect nothing,
+    so the benchmark keeps their outputs as the background (scaled to the 0.02 level of the synthetic recipe) and adds, per
+    object, the detection blob and the peaked mark rows of `make_maps`.  det (B, H, W), marks (B, 3, H, W, 32)."""
+    import torch
+
+    bsz, h, w = det.shape
+    device = det.device
+    det.mul_(0.04)
+    r = int(math.ceil(3 * blob_sigma))
+    ax = torch.arange(-r, r + 1, device=device)
+    dx, dy = torch.meshgrid(ax, ax, indexing="ij")
+    blob = (0.97 * torch.exp(-(dx ** 2 + dy ** 2).float() / (2 * blob_sigma ** 2))).reshape(1, -1)
+    axp = torch.arange(-peak_radius, peak_radius + 1, device=device)
+    dxp, dyp = torch.meshgrid(axp, axp, indexing="ij")
+    for k, objs in enumerate(objs_per_tile):
+        n = len(objs)
+        if n == 0:
+            continue
+        cx = torch.as_tensor(objs[:, 0].astype(np.int64), device=device)
+        cy = torch.as_tensor(objs[:, 1].astype(np.int64), device=device)
+        px, py = cx[:, None] + dx.reshape(1, -1), cy[:, None] + dy.reshape(1, -1)
+        ok = (px >= 0) & (px < h) & (py >= 0) & (py < w)
+        det[k].view(-1).index_put_(((px * w + py)[ok],), blob.expand(n, -1)[ok], accumulate=True)
+        cls = torch.as_tensor(mark_classes(objs), device=device)
+        px, py = cx[:, None] + dxp.reshape(1, -1), cy[:, None] + dyp.reshape(1, -1)
+        ok = (px >= 0) & (px < h) & (py >= 0) & (py < w)
+        owner = torch.full((h * w,), n, dtype=torch.int64, device=device)
+        owner.scatter_reduce_(0, (px * w + py)[ok], torch.arange(n, device=device)[:, None].expand(-1, px.shape[1])[ok], reduce="amin")
+        pix = torch.nonzero(owner < n).squeeze(1)
+        for i in range(3):
+            flat = marks[k, i].view(-1, N_CLASSES)
+            c = cls[owner[pix], i]
+            win = flat[pix]
+            rest = 1.0 - win.gather(1, c[:, None]).squeeze(1)
+            win *= ((1.0 - peak) / rest.clamp_min(1e-6))[:, None]
+            win.scatter_(1, c[:, None], peak)
+            win /= win.sum(-1, keepdim=True)
+            flat[pix] = win
+    det.clamp_(0.0, 0.999)
+    return det, marks

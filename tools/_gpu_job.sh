@@ -1,4 +1,3 @@
 cd /root/repo
-N=$1
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_r2_n$N.json 2> gpurun_out/bench_r2_n$N.err ) 2> gpurun_out/bench_r2_n$N.time
+( time timeout 900 python bench.py > gpurun_out/bench_r2_e.json 2> gpurun_out/bench_r2_e.err ) 2> gpurun_out/bench_r2_e.time
 echo done
