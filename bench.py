@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--warps", type=int, default=8, help="warps per window (speculation depth) of the window sampler")
     ap.add_argument("--sampler", default="windows", choices=["windows", "cells"],
                     help="windows: mpp_run_windows (production); cells: mpp_run_sweeps (first-generation aligned cells)")
-    ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "colours"],
+    ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "colours", "multi"],
                     help="window sampler: one persistent dataflow kernel per call, or one launch per colour class")
     ap.add_argument("--stride", type=int, default=3)
     ap.add_argument("--temperature", type=float, default=0.02)
@@ -550,9 +550,14 @@ def run_b200(args):
     n0 = len(eng)
 
     def run(n_sweeps, seed_off, read_counters=False):
+        if args.sampler == "windows" and args.schedule == "multi" and n_sweeps > 0:
+            from mpp_cnn_rs_object_detection_b200.engine import run_windows_batch
+            return run_windows_batch([eng], [args.seed + rank], n_sweeps, args.per_visit, n_warps=args.warps, t0=args.temperature,
+                                     sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
         if args.sampler == "windows":
             return eng.run_windows(n_sweeps, args.per_visit, args.warps, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
-                                   sweep_offset=seed_off * args.sweeps, read_counters=read_counters, schedule=args.schedule)
+                                   sweep_offset=seed_off * args.sweeps, read_counters=read_counters,
+                                   schedule="dataflow" if args.schedule == "multi" else args.schedule)
         return eng.run_sweeps(n_sweeps, args.per_visit, args.stride, t0=args.temperature, alpha_t=1.0, seed=args.seed + rank,
                               sweep_offset=seed_off * args.sweeps, read_counters=read_counters)
 

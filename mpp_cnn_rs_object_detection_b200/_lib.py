@@ -77,6 +77,11 @@ def load():
     if _lib is not None:
         return _lib
     path = LIB_PATH
+    if os.environ.get("MPP_B200_DEBUG") == "1" and os.environ.get("MPP_B200_DEBUG_LIB"):
+        # development only, and only when explicitly switched on: an instrumented build of the same library (tools/dbg_time.py)
+        path = os.path.abspath(os.environ["MPP_B200_DEBUG_LIB"])
+        if not path.startswith(os.path.dirname(PKG_DIR) + os.sep):
+            raise RuntimeError("MPP_B200_DEBUG_LIB must point inside the repository")
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: run `python -m mpp_cnn_rs_object_detection_b200.build` "
                            f"(the MPP sampler has no CPU fallback)")

@@ -1419,9 +1419,10 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
         if (temp > t_target) temp *= alpha_t;
     }
     base[S] = total;
-    // device layout: [ints: ox, oy, task_base | next_task | done 2*dg*dg] [floats: temp]
+    // device layout: [ints: ox, oy, task_base | next_task | done 2*dg*dg] [floats: temp] [the device view of the context]
     const size_t n_int = (size_t)3 * S + 2 + 1 + (size_t)2 * dg * dg;
-    const size_t bytes = n_int * sizeof(int) + (size_t)S * sizeof(float);
+    const size_t off_ctx = (n_int * sizeof(int) + (size_t)S * sizeof(float) + 15) & ~(size_t)15;
+    const size_t bytes = off_ctx + sizeof(Ctx<R>);
     if (bytes > h->plan_bytes) {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         cudaFree(h->d_plan);
@@ -1434,6 +1435,9 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     CUDA_TRY(cudaMemsetAsync(d_int + (size_t)3 * S + 2, 0, (1 + (size_t)2 * dg * dg) * sizeof(int), h->stream));
     CUDA_TRY(cudaMemcpyAsync(d_int, ints.data(), ((size_t)3 * S + 2) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(d_temp, temps.data(), (size_t)S * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const Ctx<R> view = device_view<R>(h);
+    Ctx<R> *d_ctx = reinterpret_cast<Ctx<R> *>(reinterpret_cast<unsigned char *>(h->d_plan) + off_ctx);
+    CUDA_TRY(cudaMemcpyAsync(d_ctx, &view, sizeof(Ctx<R>), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
     SweepPlan plan;
     plan.n_sweeps = S; plan.total_tasks = total; plan.dg = dg;
@@ -1442,7 +1446,7 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     const uint32_t uid_base = h->window_uid_next;
     h->window_uid_next += (uint32_t)total * (uint32_t)per_visit;
     if (h->window_uid_next < 0x80000000u) h->window_uid_next += 0x80000000u;
-    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (size_t)NW * W2_SCRATCH * sizeof(R);
+    const size_t smem = ((sizeof(WinState<R>) + 15) & ~(size_t)15) + (((size_t)NW * W2_SCRATCH * sizeof(R) + 15) & ~(size_t)15) + sizeof(Ctx<R>);
     static int blocks_per_sm_dev[MPP_MAX_DEVICES] = {};  // per device: shared-memory opt-in + occupancy of this instantiation
     if (!blocks_per_sm_dev[h->device]) {
         int bps = 0;
@@ -1457,9 +1461,10 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     // so that small scenes leave room for other contexts' kernels running concurrently on other streams (waiting CTAs
     // occupy SM slots: 32 tiles of 512^2 ran at 46 M proposals/s with two colour classes of CTAs each, 103 M/s with half a class)
     const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
-    const int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
+    int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
+    if (getenv("MPP_TUNE_CAP_X4")) cap_x4 = std::max(1, atoi(getenv("MPP_TUNE_CAP_X4")));  // TUNING ONLY (removed before commit)
     const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_x4 * per_colour / 4 + 8));
-    k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(device_view<R>(h), plan, per_visit, seed, sweep_offset, uid_base, dbg);
+    k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(d_ctx, plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
     return MPP_OK;
 }

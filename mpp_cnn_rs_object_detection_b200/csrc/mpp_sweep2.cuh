@@ -164,8 +164,20 @@ __device__ __noinline__ void recompute_top2(const ModelDev &m, WinState<R> &w, i
     if (do_al) { w.al1[k] = a1; w.al2[k] = a2; w.aal[k] = (short)aa; w.aal2[k] = (short)aa2; }
 }
 
+#ifdef MPP_V_FOBJ
+#define MPP_FOBJ_INL __noinline__
+#else
+#define MPP_FOBJ_INL __forceinline__
+#endif
+// (out of line: three inlined copies of the unrolled 32-step scan cost 2 % through instruction-cache misses)
+#define MPP_SCAN_INL __noinline__
+#ifdef MPP_V_DELTA
+#define MPP_DELTA_INL __noinline__
+#else
+#define MPP_DELTA_INL
+#endif
 template <typename R>
-__device__ __forceinline__ R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
+__device__ MPP_FOBJ_INL R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
     Terms<R> t;
     t.pos = w.pos[k]; t.m0 = w.tm0[k]; t.m1 = w.tm1[k]; t.m2 = w.tm2[k];
     t.ov = ov; t.al = (m.rewarding ? (R)-1 : (R)1) * al;
@@ -178,7 +190,7 @@ __device__ __forceinline__ R f_obj(const ModelDev &m, const WinState<R> &w, int 
 // po / pa (per-warp scratch, W2_K entries each) receive the overlap / alignment pair values between every staged
 // entry and `a` (0 where out of reach) so that an accepted proposal can update the top-2 reductions incrementally.
 template <typename R>
-__device__ R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy, R *po, R *pa) {
+__device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy, R *po, R *pa) {
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
     const R rad_a = has_add ? r_sqrt(a.hl * a.hl + a.hw * a.hw) : (R)0;
     const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
@@ -602,19 +614,42 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
     bool any_pair = false;
     for (int k = lane; k < n; k += 32) {
         if (k == s || !(w.flags[k] & W2_ALIVE)) continue;
-        // the removed object was this entry's best or second-best partner: its top-2 must be rescanned
-        const bool redo_ov = r >= 0 && (w.aov[k] == r || w.aov2[k] == r), redo_al = r >= 0 && (w.aal[k] == r || w.aal2[k] == r);
+        // the removed object was this entry's best or second-best partner: its top-2 must be rescanned -- unless the object is
+        // REPLACED in the same staged slot (a move: s == r) and its new pair value keeps its place: then only the value changes.
+        // (Most accepted moves are mark transforms that leave the alignment value with every neighbour as it was.)
+        bool redo_ov = r >= 0 && (w.aov[k] == r || w.aov2[k] == r), redo_al = r >= 0 && (w.aal[k] == r || w.aal2[k] == r);
+        const bool was_ov = redo_ov && s == r, was_al = redo_al && s == r;  // r held a place in this entry's top-2 and is being replaced
+        const R o = s >= 0 ? po[k] : (R)0, al = s >= 0 ? pa[k] : (R)0;
+        if (s >= 0 && s == r && (w.flags[k] & W2_INNER)) {
+            if (redo_ov) {
+                if (w.aov[k] == r) {  // was the best partner
+                    if (o > (R)0 && o >= w.ov2[k]) { w.ov1[k] = o; redo_ov = false; }
+                    else if (!(o > (R)0) && !(w.ov2[k] > (R)0)) { w.ov1[k] = 0; w.aov[k] = -1; redo_ov = false; }
+                } else {  // was the second best
+                    if (o > w.ov1[k]) { const R t1 = w.ov1[k]; const short a1 = w.aov[k]; w.ov1[k] = o; w.aov[k] = (short)s; w.ov2[k] = t1; w.aov2[k] = a1; redo_ov = false; }
+                    else if (o > (R)0 && o >= w.ov2[k]) { w.ov2[k] = o; redo_ov = false; }
+                }
+            }
+            if (redo_al) {
+                if (w.aal[k] == r) {
+                    if (al > (R)0 && al >= w.al2[k]) { w.al1[k] = al; redo_al = false; }
+                    else if (!(al > (R)0) && !(w.al2[k] > (R)0)) { w.al1[k] = 0; w.aal[k] = -1; redo_al = false; }
+                } else {
+                    if (al > w.al1[k]) { const R t1 = w.al1[k]; const short a1 = w.aal[k]; w.al1[k] = al; w.aal[k] = (short)s; w.al2[k] = t1; w.aal2[k] = a1; redo_al = false; }
+                    else if (al > (R)0 && al >= w.al2[k]) { w.al2[k] = al; redo_al = false; }
+                }
+            }
+        }
         if (s >= 0) {
-            const R o = po[k], al = pa[k];
             if (o > (R)0 || al > (R)0) {  // isolated objects (the common case) skip all of this
                 any_pair = true;
                 if (o > n_o1) { n_o2 = n_o1; n_ao2 = n_ao; n_o1 = o; n_ao = k; } else if (o > n_o2) { n_o2 = o; n_ao2 = k; }
                 if (al > n_a1) { n_a2 = n_a1; n_aa2 = n_aa; n_a1 = al; n_aa = k; } else if (al > n_a2) { n_a2 = al; n_aa2 = k; }
-                if (!redo_ov && (w.flags[k] & W2_INNER)) {
+                if (!redo_ov && !was_ov && (w.flags[k] & W2_INNER)) {
                     if (o > w.ov1[k]) { w.ov2[k] = w.ov1[k]; w.aov2[k] = w.aov[k]; w.ov1[k] = o; w.aov[k] = (short)s; }
                     else if (o > w.ov2[k]) { w.ov2[k] = o; w.aov2[k] = (short)s; }
                 }
-                if (!redo_al && (w.flags[k] & W2_INNER)) {
+                if (!redo_al && !was_al && (w.flags[k] & W2_INNER)) {
                     if (al > w.al1[k]) { w.al2[k] = w.al1[k]; w.aal2[k] = w.aal[k]; w.al1[k] = al; w.aal[k] = (short)s; }
                     else if (al > w.al2[k]) { w.al2[k] = al; w.aal2[k] = (short)s; }
                 }
@@ -671,14 +706,14 @@ __device__ __forceinline__ int scan32(const float *v, int n, float target, float
     *picked = lastv;
     return last;
 }
-__device__ __forceinline__ int scan_pick_global(const float *row, int n, float target, float *picked) {
+__device__ MPP_SCAN_INL int scan_pick_global(const float *row, int n, float target, float *picked) {
     float v[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = k < n ? __ldg(row + k) : 0.f;
     return scan32(v, n, target, picked);
 }
 // ... over one 128-byte aligned mark row (32 classes): eight 16-byte loads
-__device__ __forceinline__ int scan_pick_row(const float *row, float target, float *picked) {
+__device__ MPP_SCAN_INL int scan_pick_row(const float *row, float target, float *picked) {
     float v[32];
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll
@@ -1540,11 +1575,20 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 #define MPP_DF_MIN_BLOCKS 2
 #endif
 template <typename R, int NW, bool DBG, bool SIMT>
-__global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow(Ctx<R> c, SweepPlan plan, int per_visit, uint64_t seed, uint64_t sweep_offset,
-                                                             uint32_t uid_base, float *dbg_maxdiff) {
+__global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow(const Ctx<R> *__restrict__ ctx_global, SweepPlan plan, int per_visit, uint64_t seed,
+                                                             uint64_t sweep_offset, uint32_t uid_base, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
     WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
-    R *scratch = reinterpret_cast<R *>(smem + ((sizeof(WinState<R>) + 15) & ~(size_t)15));
+    constexpr size_t WS = (sizeof(WinState<R>) + 15) & ~(size_t)15, SC = ((size_t)NW * W2_SCRATCH * sizeof(R) + 15) & ~(size_t)15;
+    R *scratch = reinterpret_cast<R *>(smem + WS);
+    // the context lives in shared memory: as a by-value kernel parameter it was copied to a ~1 KB local stack frame (its
+    // address is taken for the out-of-line helpers), which cost 5 % of the throughput
+    Ctx<R> &c = *reinterpret_cast<Ctx<R> *>(smem + WS + SC);
+    {
+        const int *src = reinterpret_cast<const int *>(ctx_global);
+        int *dst = reinterpret_cast<int *>(&c);
+        for (int k = threadIdx.x; k < (int)(sizeof(Ctx<R>) / 4); k += 32 * NW) dst[k] = src[k];
+    }
     __shared__ int s_task;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {

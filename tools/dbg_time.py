@@ -12,7 +12,7 @@ Cc, H = bench.CALIB_HRCM, bench.HRC
 spec = ModelSpec(setup="legacy", pos_threshold=Cc["detection_threshold"], remap_coefs=Cc["coefs"], remap_intercepts=Cc["intercepts"],
                  min_area=Cc["min_area"], max_area=Cc["max_area"], combinator="hierarchical",
                  comb_w=list(H["weights_data"]) + list(H["weights_prior"]) + list(H["data_prior_weights"]) + [0.0])
-for nw, pv in ((8, 64),):
+for nw, pv in ((8, 96),):
     eng = Engine((size, size), device=dev)
     eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
     eng.add_objects(objs[:, :2], objs[:, 2:5])
@@ -24,6 +24,13 @@ for nw, pv in ((8, 64),):
     n = min(4000, int(d[1:2].view(np.int32)[0]))
     tr = d[8:8 + n * 12].reshape(n, 12)
     print(f"nw={nw} pv={pv}: visits traced {n}")
+    occ = tr[:, 1] > 0
+    for label, sel in (("empty windows", ~occ), ("occupied windows", occ), ("windows with >= 3 objects", tr[:, 1] >= 3)):
+        t = tr[sel]
+        if len(t):
+            print(f"  [{label}: {len(t)} visits] total us mean {t[:, 10].mean() / 1900:.1f} p90 {np.percentile(t[:, 10], 90) / 1900:.1f} | staging (A..E) "
+                  f"{(t[:, 2] + t[:, 3] + t[:, 4] + t[:, 5]).mean() / 1900:.1f} | eval {t[:, 6].mean() / 1900:.1f} | commit {t[:, 7].mean() / 1900:.1f} | rounds {t[:, 8].mean():.1f} | "
+                  f"accepted {t[:, 9].mean():.1f} | staged n {t[:, 0].mean():.1f} | n_win {t[:, 1].mean():.2f}")
     for name, col in (("staged n", 0), ("n_win", 1), ("A heads us", 2), ("B rank us", 3), ("C recs us", 4), ("D+E us", 5), ("eval us", 6), ("commit us", 7),
                       ("rounds", 8), ("acc", 9), ("total us", 10), ("evaluated", 11)):
         v = tr[:, col] / 1900.0 if "us" in name else tr[:, col]
