@@ -1461,8 +1461,7 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     // so that small scenes leave room for other contexts' kernels running concurrently on other streams (waiting CTAs
     // occupy SM slots: 32 tiles of 512^2 ran at 46 M proposals/s with two colour classes of CTAs each, 103 M/s with half a class)
     const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
-    int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
-    if (getenv("MPP_TUNE_CAP_X4")) cap_x4 = std::max(1, atoi(getenv("MPP_TUNE_CAP_X4")));  // TUNING ONLY (removed before commit)
+    const int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
     const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_x4 * per_colour / 4 + 8));
     k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(d_ctx, plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
