@@ -226,6 +226,13 @@ int mpp_sample_proposals(mpp_ctx *ctx, const int32_t *kernel_ids, int m, uint64_
  * state: out [m][2] = {forward, backward}. */
 int mpp_proposal_probs(mpp_ctx *ctx, const mpp_proposal *props, int m, double *out);
 
+/* utils/sampler2d.py:5-48 sample_point_2d(density=...): n pixel draws (with replacement) with probability proportional to a
+ * non-negative density map (height, width) f32 on the device: row prefix sums + inverse CDF (row, then column), Philox4x32-10
+ * keyed by (seed, draw index).  out_xy [n][2] int32 (row, column).  scratch: device doubles, height * (width + 1) + height.
+ * No context needed (the data-driven birth of a context uses its own per-cell CDF: mpp_sample_births). */
+int mpp_sample_points_2d(const float *density, int height, int width, int n, uint64_t seed, int32_t *out_xy, double *scratch,
+                         int device, void *stream);
+
 /* EnergyCombinationModel.compute (custom_types/energy.py:8-11) on device for n per-object energy vectors
  * [n][MPP_MAX_TERMS] (term order of the setup): out_per_object [n] (may be NULL), out_total [1].  No ctx needed. */
 int mpp_combine(const mpp_model_params *model_host, const double *vectors, int n, double *out_per_object,

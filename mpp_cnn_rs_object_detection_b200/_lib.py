@@ -60,7 +60,7 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
            "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid",
            "mpp_set_window_trace", "mpp_window_stats", "mpp_run_windows_batch", "mpp_split_export", "mpp_split_attach",
-           "mpp_split_attach_local", "mpp_split_detach", "mpp_set_maps_band"]
+           "mpp_split_attach_local", "mpp_split_detach", "mpp_set_maps_band", "mpp_sample_points_2d"]
 
 _lib = None
 
@@ -78,7 +78,7 @@ def load():
         return _lib
     path = LIB_PATH
     if os.environ.get("MPP_B200_DEBUG") == "1" and os.environ.get("MPP_B200_DEBUG_LIB"):
-        # development only, and only when explicitly switched on: an instrumented build of the same library (tools/dbg_time.py)
+        # development only, and only when explicitly switched on: an instrumented build of the same library (tools/visit_timers.py)
         path = os.path.abspath(os.environ["MPP_B200_DEBUG_LIB"])
         if not path.startswith(os.path.dirname(PKG_DIR) + os.sep):
             raise RuntimeError("MPP_B200_DEBUG_LIB must point inside the repository")
@@ -95,6 +95,7 @@ def load():
     lib.mpp_ctx_destroy.argtypes = [vp]
     lib.mpp_ctx_reset.argtypes = [vp, vp]
     lib.mpp_set_maps.argtypes = [vp, vp, vp, f64]
+    lib.mpp_sample_points_2d.argtypes = [vp, i32, i32, i32, u64, vp, vp, i32, vp]
     lib.mpp_set_maps_band.argtypes = [vp, vp, vp, i32, i32, f64]
     lib.mpp_set_model.argtypes = [vp, C.POINTER(ModelParams)]
     lib.mpp_set_kernels.argtypes = [vp, C.POINTER(KernelParams)]

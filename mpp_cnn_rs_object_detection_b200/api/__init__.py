@@ -19,7 +19,8 @@ from .perturbation_sampler import (PERTURBATION_HP_MEDIUM, PERTURBATION_LIGHT, P
                                    PERTURBATION_STRONG, aggregate_perturbations, sample_kernel_perturbations,
                                    sample_multiple_kernel_perturbations, sample_perturbations)
 from .point_set import PointsSet  # noqa: F401
-from .rjmcmc import RJMCMC, StopOnMaxIter, naive_detection, nms_distance, sample_rjmcmc, sample_rjmcmc_batch, sample_rjmcmc_tiles  # noqa: F401
+from .rjmcmc import RJMCMC, RJMCMCTimer, StopOnMaxIter, naive_detection, nms_distance, sample_rjmcmc, sample_rjmcmc_batch, sample_rjmcmc_tiles  # noqa: F401
+from .sampler2d import sample_point_2d  # noqa: F401
 from .shapes import Point, Rectangle, polygon_to_abw, rect_to_poly, rotation_matrix, sra_to_wla, wla_to_sra  # noqa: F401
 from .mpp_model import (MPPModel, combinator_from_manual_config, crop_image_w_maps, labels_to_rectangles, load_energy_combination_model,  # noqa: F401
                         load_image_w_maps, merge_patches, resolve_model_config_path, restricted_load)

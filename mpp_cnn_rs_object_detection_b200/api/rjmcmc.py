@@ -13,7 +13,7 @@ import logging
 import time
 import warnings
 from dataclasses import dataclass
-from typing import Callable, List, Tuple, Union
+from typing import Callable, Dict, List, Tuple, Union
 
 import numpy as np
 
@@ -47,6 +47,41 @@ class StopOnMaxIter(StoppingCondition):  # stopping.py:37-45
 
 
 # ---------------------------------------------------------------------------------------------- rjmcmc.py
+class RJMCMCTimer:
+    """Per-stage wall-clock of the step-by-step chain, same interface and stage names as the reference (rjmcmc.py:18-48):
+    `timings` maps 'sample_kernel', 'sample_perturbation', 'compute_energy', 'compute_alpha', 'apply_perturbation', 'log' to
+    one duration per step, plus 'total' and 'n_points'.  Every stage is a call into the device library here, so a duration is
+    launch + synchronisation latency, not CPU arithmetic.  The device-resident chains (the sequential chain run as one kernel
+    and the window sampler) have no host stages: they add one 'total' entry per launch and report their counters through
+    sample_rjmcmc(return_stats=True) / mpp_window_stats."""
+
+    def __init__(self):
+        self.last_tick = None
+        self.timings: Dict[str, List[float]] = {"total": [], "n_points": []}
+        self.start_tick = None
+
+    def start_step(self):
+        self.start_tick = time.perf_counter()
+        self.last_tick = self.start_tick
+
+    def checkpoint(self, key):
+        now = time.perf_counter()
+        self.timings.setdefault(key, []).append(now - self.last_tick)
+        self.last_tick = now
+
+    def end_step(self, n_points):
+        self.timings["total"].append(time.perf_counter() - self.start_tick)
+        self.timings["n_points"].append(n_points)
+
+    def show_results(self):
+        points_number = np.array(self.timings["n_points"])
+        for k, l in self.timings.items():
+            if k != "n_points":
+                l = np.array(l)
+                per_point = l[:len(points_number)][points_number[:len(l)] > 0] / points_number[:len(l)][points_number[:len(l)] > 0] if len(l) else l
+                print(f"{k:20}: {np.mean(l) if len(l) else 0.0:.2e} s | {np.mean(per_point) if len(per_point) else 0.0:.2e} s/point")
+
+
 @dataclass
 class RJMCMC:
     t0: float
@@ -70,26 +105,41 @@ class RJMCMC:
         self._iter: int = 0
         self._state_log: List[EPointsSet] = [self.initial_state]
         self._state_summaries: List[RJMCMCStateSummary] = [RJMCMCStateSummary(n_points=len(self.initial_state), iter=self._iter)]
+        self._timer = RJMCMCTimer()
+
+    def get_timings(self) -> RJMCMCTimer:
+        """rjmcmc.py:183-184."""
+        return self._timer
+
+    def get_state_log(self):
+        """rjmcmc.py:186-187."""
+        return self._state_log
 
     def step(self, return_state=False):
         """One Metropolis-Hastings-Green step (rjmcmc.py:83-164)."""
         if self.stopping_condition.do_stop(self._state_summaries):
             raise StopIteration
+        self._timer.start_step()
         k1: Kernel = self.kernels[int(self.rng.choice(len(self.kernels), p=self.p_kernels))]
+        self._timer.checkpoint("sample_kernel")
         x0 = self._state_log[-1]
         u1 = k1.sample_perturbation(x0.points, self.rng)
+        self._timer.checkpoint("sample_perturbation")
         energy_x0 = self._state_summaries[-1].energy
         if energy_x0 is None:
             energy_x0 = x0.total_energy()  # raw sum on the first iteration (rjmcmc.py:96-98)
         energy_delta = x0.energy_delta(u1, energy_combinator=self.energy_combinator)
         energy_x1 = energy_x0 + energy_delta
+        self._timer.checkpoint("compute_energy")
         log_alpha_1 = (-energy_delta / self._temp) + np.log(k1.backward_probability(x0.points, u1) + EPS) \
             - np.log(k1.forward_probability(x0.points, u1) + EPS)
         accepted = bool(np.log(self.rng.random() + EPS) < log_alpha_1)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             alpha_1 = float(np.exp(log_alpha_1))
+        self._timer.checkpoint("compute_alpha")
         x1 = x0.apply_perturbation(u1, inplace=True) if accepted else x0
+        self._timer.checkpoint("apply_perturbation")
         summary = RJMCMCStateSummary(iter=self._iter, temperature=self._temp, energy=energy_x1 if accepted else energy_x0,
                                      n_points=len(x1), kernel=k1.__class__, move_accepted=accepted, alpha=alpha_1,
                                      initial_energy=energy_x0, proposed_energy=energy_x1)
@@ -101,6 +151,8 @@ class RJMCMC:
         self._iter += 1
         if self.do_annealing and self._temp > self.t_target:
             self._temp *= self.alpha_t
+        self._timer.checkpoint("log")
+        self._timer.end_step(n_points=len(x1))
         if return_state:
             return summary, x1.copy()
         return summary
@@ -158,10 +210,15 @@ class RJMCMC:
 
     def run(self, show_timing=False) -> Tuple[Union[List[EPointsSet], EPointsSet], List[RJMCMCStateSummary]]:
         if self._device_chain_possible() and self.verbose == 0:
+            self._timer.start_step()
             self._run_on_device()
+            self._timer.end_step(n_points=len(self._state_log[-1]))
         else:
             for _ in self.__iter__():
                 pass
+        if show_timing:
+            print("Timings--------------------------------------------------------------------------")
+            self._timer.show_results()
         return self._state_log, self._state_summaries
 
 
@@ -250,6 +307,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         states, _ = chain.run()
         result = [states[-1].points] if num_samples == 1 else [s.points for s in states[-num_samples:]]
     elif sampler == "parallel":
+        import torch
+        torch.cuda.nvtx.range_push("mpp.sample_rjmcmc.windows")  # NVTX: visible in Nsight Systems timelines
         kernels[0]._kset.bind(points.points)
         st.use_combinator(energy_combinator)
         eng = st.engine
@@ -279,6 +338,8 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
                 st.refresh_from_device()
                 points.energy_graph._members = dict.fromkeys(st.handle_of)
                 states.append(points.copy())
+
+        torch.cuda.nvtx.range_pop()
 
         def finish():
             if return_stats:

@@ -998,6 +998,44 @@ int mpp_set_maps(mpp_ctx *h, const float *det, const float *marks, double det_su
     return MPP_OK;
 }
 
+// ---- utils/sampler2d.py:5-48: weighted pixel draws from a density map (stand-alone: no context needed) ------
+__global__ void k_row_totals(const double *__restrict__ rowcum, int H, int W, double *__restrict__ tot) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < H) tot[r] = rowcum[(size_t)r * ((size_t)W + 1) + W];
+}
+__global__ void k_sample_points_2d(const double *__restrict__ rowcum, const double *__restrict__ row_cdf, int H, int W, int n, uint64_t seed,
+                                   int32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Philox rng(seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0x5a2d0000u);
+    const uint4 q = rng.next();
+    // inverse CDF: first row whose inclusive prefix exceeds u * total, then first column of that row likewise
+    // (numpy Generator.choice: cdf = cumsum(p); searchsorted(u * cdf[-1], side='right'))
+    const double t = u01(q.x, q.y) * row_cdf[H - 1];
+    int lo = 0, hi = H - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (row_cdf[mid] > t) hi = mid; else lo = mid + 1; }
+    const double *rc = rowcum + (size_t)lo * ((size_t)W + 1);
+    const double tc = u01(q.z, q.w) * rc[W];
+    int a = 0, b = W - 1;
+    while (a < b) { const int mid = (a + b) >> 1; if (rc[mid + 1] > tc) b = mid; else a = mid + 1; }
+    out[2 * i] = lo; out[2 * i + 1] = a;
+}
+
+int mpp_sample_points_2d(const float *density, int height, int width, int n, uint64_t seed, int32_t *out_xy, double *scratch, int device,
+                         void *stream) {
+    if (!density || !out_xy || !scratch || height < 1 || width < 1 || n < 0) return fail(MPP_ERR_INVALID, "mpp_sample_points_2d: bad arguments");
+    if (n == 0) return MPP_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double *rowcum = scratch, *row_cdf = scratch + (size_t)height * ((size_t)width + 1);
+    k_row_prefix<<<(height + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(density, height, width, rowcum);
+    k_row_totals<<<(height + 255) / 256, 256, 0, st>>>(rowcum, height, width, row_cdf);
+    k_scan_double<<<1, 1024, 0, st>>>(row_cdf, height);
+    k_sample_points_2d<<<(n + 127) / 128, 128, 0, st>>>(rowcum, row_cdf, height, width, n, seed, out_xy);
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
 __global__ void k_set_inv_total(double *cdf, int n, double total) { cdf[n] = total > 0.0 ? 1.0 / total : 0.0; }
 
 int mpp_set_maps_band(mpp_ctx *h, const float *det_band, const float *marks_band, int row0, int rows, double det_sum_scene) {

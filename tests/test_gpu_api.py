@@ -469,3 +469,62 @@ def test_training_helpers_energy_vectors_and_kernel_walks():
     net = api.aggregate_perturbations(seq)
     want = (set(start) - set(net.removal)) | set(net.addition)
     assert set(end) == want and isinstance(agg.removal, list) and isinstance(agg.addition, list)
+
+
+def test_sample_point_2d_export():
+    """utils/sampler2d.py:5-48 through the device inverse-CDF sampler: signature, shapes, distribution, without replacement."""
+    import mpp_cnn_rs_object_detection_b200.api as api
+    rng = np.random.default_rng(3)
+    shape = (37, 53)
+    dens = rng.random(shape).astype(np.float32) ** 3
+    dens[5:9, :] = 0.0
+    pts = api.sample_point_2d(shape, size=1, density=dens, rng=rng)
+    assert pts.shape == (1, 2) and dens[pts[0, 0], pts[0, 1]] > 0
+    uni = api.sample_point_2d(shape, size=5, rng=rng)
+    assert uni.shape == (5, 2) and np.all((uni >= 0) & (uni < np.array(shape)))
+    # many single draws: chi-square against the density, coarsened to row bands
+    n = 20000
+    from mpp_cnn_rs_object_detection_b200.api.sampler2d import _device_draws
+    d = _device_draws(dens, shape, n, seed=11)
+    assert np.all(dens[d[:, 0], d[:, 1]] > 0)
+    want = dens.reshape(-1) / dens.sum()
+    got = np.bincount(d[:, 0] * shape[1] + d[:, 1], minlength=shape[0] * shape[1]) / n
+    band = lambda v: v.reshape(shape).sum(1)  # noqa: E731
+    e, o = band(want) * n, band(got) * n
+    keep = e > 5
+    chi2 = float(np.sum((o[keep] - e[keep]) ** 2 / e[keep]))
+    assert chi2 < 2.5 * keep.sum(), (chi2, keep.sum())
+    # without replacement: all pixels of a tiny support come out exactly once
+    small = np.zeros(shape, dtype=np.float32)
+    small[3, 4], small[10, 11], small[20, 1] = 0.7, 0.2, 0.1
+    allp = api.sample_point_2d(shape, size=3, density=small, rng=rng)
+    assert sorted(map(tuple, allp.tolist())) == [(3, 4), (10, 11), (20, 1)]
+    with pytest.raises(ValueError):
+        api.sample_point_2d(shape, size=4, density=small, rng=rng)
+    # mask semantics of the reference: density[mask] = 0
+    mask = np.zeros(shape, dtype=bool)
+    mask[3, 4] = True
+    two = api.sample_point_2d(shape, size=2, density=small.copy(), rng=rng, mask=mask)
+    assert sorted(map(tuple, two.tolist())) == [(10, 11), (20, 1)]
+
+
+def test_rjmcmc_timer_interface():
+    """RJMCMC.get_timings() / get_state_log() with the reference's stage names (rjmcmc.py:18-48,183-187)."""
+    import mpp_cnn_rs_object_detection_b200.api as api
+    from mpp_cnn_rs_object_detection_b200 import synth
+    objs, det, marks = synth.make_scene(4, (64, 96), 10)
+    img = api.ImageWMaps("t", (64, 96), None, det, marks, api.default_mappings(), ["size", "ratio", "angle"])
+    setup = api.LegacyEnergySetup(calibration_params={}, energy_calibration=api.LegacyEnergiesCalibration(
+        gu.CALIB_HRCM["detection_threshold"], list(gu.CALIB_HRCM["coefs"]), list(gu.CALIB_HRCM["intercepts"]), gu.CALIB_HRCM["min_area"], gu.CALIB_HRCM["max_area"]))
+    unit, pair = setup.make_energies(img)
+    pts = api.EPointsSet([api.Rectangle(int(o[0]), int(o[1]), float(o[2]), float(o[3]), float(o[4])) for o in objs], img.shape, unit, pair)
+    rng = np.random.default_rng(0)
+    kernels, p = api.make_kernels(img, intensity=len(objs), rng=rng)
+    chain = api.RJMCMC(t0=0.1, kernels=kernels, p_kernels=p, initial_state=pts, stopping_condition=api.StopOnMaxIter(40), rng=rng, alpha_t=0.99, verbose=1)
+    chain.run()
+    t = chain.get_timings()
+    assert isinstance(t, api.RJMCMCTimer)
+    for key in ("sample_kernel", "sample_perturbation", "compute_energy", "compute_alpha", "apply_perturbation", "log", "total", "n_points"):
+        assert key in t.timings and len(t.timings[key]) == 41, (key, len(t.timings.get(key, [])))
+    assert all(v >= 0 for v in t.timings["total"]) and len(chain.get_state_log()) >= 1
+    t.show_results()

@@ -35,11 +35,13 @@ def _recall_precision(centers, objs, tol=3):
     return float((d.min(0) <= tol).mean()), float((d.min(1) <= tol).mean())
 
 
-@pytest.mark.parametrize("pid", [2781, 2789])
+@pytest.mark.parametrize("pid,budget", [(2781, 1), (2789, 1), (2794, 1), (2781, 4)])
 @pytest.mark.parametrize("name", ["mpp_hrcM", "mpp_log"])
-def test_named_configs_on_val_annotations(name, pid):
+def test_named_configs_on_val_annotations(name, pid, budget):
+    """budget: multiple of the shipped burn-in (30 000 steps per 256^2 patch, model_configs/mpp/*.json)."""
     import mpp_cnn_rs_object_detection_b200.api as api
     cfg = json.load(open(os.path.join(GOLD, f"model_{name}", "config.json")))
+    cfg["inference"]["rjmcmc_params"]["burn_in"] = int(cfg["inference"]["rjmcmc_params"]["burn_in"]) * budget
     if name == "mpp_hrcM":
         model = api.MPPModel(cfg, model_dir=os.path.join(GOLD, "model_mpp_hrcM"))  # manual weights from the config JSON
     else:
@@ -52,10 +54,12 @@ def test_named_configs_on_val_annotations(name, pid):
     img, objs = _val_image(api, pid)
     res = model.infer_image(img)
     recall, precision = _recall_precision(res["detection_center"], objs)
-    print(f"\n{name} on {pid} {img.shape}: {len(objs)} annotated, {len(res['detection_center'])} found, recall {recall:.3f}, precision {precision:.3f}")
+    print(f"\n{name} on {pid} {img.shape} budget x{budget}: {len(objs)} annotated, {len(res['detection_center'])} found, recall {recall:.3f}, precision {precision:.3f}")
     # the dense parking lot of image 2781 (272 vehicles on 469x753) is not fully recovered within the reference's budget by
-    # EITHER sampler: parallel 0.78-0.84, device sequential chain 0.76-0.81, both ~0.95 with 4x the budget (tools/dbg_cfg.py)
-    assert recall > 0.7 and precision > 0.8, (recall, precision)
+    # EITHER sampler (parallel 0.78-0.84, device sequential chain 0.76-0.81); with 4x the budget both exceed 0.9.  The two
+    # sparser images are recovered at the shipped budget.
+    bar = 0.7 if (pid == 2781 and budget == 1) else 0.9
+    assert recall > bar and precision > 0.9, (recall, precision, bar)
     assert len(res["detection_score"]) == len(res["detection_center"])
 
 

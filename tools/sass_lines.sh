@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: tools/sass_lines.sh <mangled kernel name> : static SASS instruction count per source line
-cd /root/repo; cuobjdump -xelf all mpp_cnn_rs_object_detection_b200/libmpp_b200.so >/dev/null 2>&1
+cd "$(dirname "$0")/.."; cuobjdump -xelf all mpp_cnn_rs_object_detection_b200/libmpp_b200.so >/dev/null 2>&1
 nvdisasm -g mpp_b200.sm_100a.cubin 2>/dev/null | python3 -c "
 import sys,re,collections
 cur=None; cnt=collections.Counter(); fn=None

@@ -1,4 +1,10 @@
-"""Per-visit phase timing of the window sampler (needs a library built with -DMPP_TRACE; development tool)."""
+"""Per-visit phase timing of the window sampler (development tool).  Needs an instrumented build of the library:
+
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -DMPP_TRACE \
+         -o tools/_trace_build.so mpp_cnn_rs_object_detection_b200/csrc/mpp_b200.cu
+    MPP_B200_DEBUG=1 MPP_B200_DEBUG_LIB=tools/_trace_build.so python tools/visit_timers.py
+
+(the library override is only honoured with MPP_B200_DEBUG=1 and for paths inside the repository)."""
 import sys, os, ctypes as C
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
