@@ -130,11 +130,27 @@ typedef struct {
     int32_t n_after;
 } mpp_step_result;
 
+/* One split (kind 8) or merge (kind 9) perturbation (Perturbation of SplitKernel / MergeKernel,
+ * rjmcmc_sampler/kernels/split_and_merge_kernels.py:39-178: one removal and two additions, or two removals and one addition,
+ * plus the kernels' `data` dict: pos_delta, shape_delta, n_neighbors). */
+typedef struct {
+    int32_t kind;            /* 8 split, 9 merge */
+    int32_t n_neighbors;     /* merge: objects within the radius of the first removal (-1: not drawn) */
+    int32_t n_add;           /* additions: 2 (split), 1 (merge), 0 (empty perturbation) */
+    int32_t reserved;
+    uint32_t rem_uid[2];     /* MPP_NO_OBJECT when absent */
+    int32_t rem_x[2], rem_y[2];
+    int32_t add_x[2], add_y[2];
+    double add_size[2], add_ratio[2], add_angle[2];
+    double pos_delta[2], shape_delta[3];
+    double u;                /* a fresh uniform for the accept test */
+} mpp_split_merge;
+
 /* ---------------------------------------------------------------------------------------------- library */
 int mpp_abi_version(void);
 const char *mpp_last_error(void);
 /* sizeof of the ABI structs as compiled: 0 mpp_model_params, 1 mpp_kernel_params, 2 mpp_proposal, 3 mpp_step_result,
- * 4 mpp_window_trace */
+ * 4 mpp_window_trace, 5 mpp_split_merge */
 int mpp_abi_struct_size(int which);
 
 /* ---------------------------------------------------------------------------------------------- context
@@ -221,6 +237,18 @@ int mpp_run_chain(mpp_ctx *ctx, int n_steps, double t0, double alpha_t, double t
  * state (nothing is applied): kernel_ids [m] (device; entry < 0: the kernel itself is drawn with p_kernel,
  * rjmcmc.py:88) -> out [m] proposals (device) whose `u` field holds a fresh accept uniform. */
 int mpp_sample_proposals(mpp_ctx *ctx, const int32_t *kernel_ids, int m, uint64_t seed, uint64_t offset, mpp_proposal *out);
+
+/* SplitKernel / MergeKernel.sample_perturbation (split_and_merge_kernels.py:51-74, 125-149) against the current state, on the
+ * device: uniform pick of an object; split: position delta uniform on the quarter disc of `radius` (the reference's rejection
+ * loop), three normal shape deltas of standard deviation shape_sigmas_host[i] * range_i, the two children clipped to the
+ * support and to the mark ranges; merge: a uniformly drawn neighbour within `radius` (Euclidean; neighbours taken in
+ * (x, y, uid) order), the merged object being the average.  Philox keyed by (seed, offset).  out: ONE record (device). */
+int mpp_sample_split_merge(mpp_ctx *ctx, int kind, double radius, const double *shape_sigmas_host, uint64_t seed, uint64_t offset,
+                           mpp_split_merge *out);
+/* SplitKernel / MergeKernel.forward_probability / backward_probability (split_and_merge_kernels.py:76-107, 151-178) of ONE
+ * perturbation (device) against the current state: out [2] = {forward, backward} (device). */
+int mpp_split_merge_probs(mpp_ctx *ctx, const mpp_split_merge *perturbation, double p_split, double p_merge, double radius,
+                          const double *shape_sigmas_host, double *out);
 
 /* Kernel.forward_probability / backward_probability (base_kernels.py:22-28) of m proposals against the current
  * state: out [m][2] = {forward, backward}. */

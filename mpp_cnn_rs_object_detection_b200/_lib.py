@@ -52,6 +52,11 @@ WINDOW_TRACE_DTYPE = np.dtype([("flags", "<u4"), ("rem_uid", "<u4"), ("add_uid",
 TRACE_WRITTEN, TRACE_EVALUATED, TRACE_ACCEPT, TRACE_IDENTITY, TRACE_HAS_ADD, TRACE_HAS_REM, TRACE_LEFT_WINDOW, TRACE_CELL_FULL = \
     1, 2, 4, 8, 16, 32, 64, 128
 
+SPLIT_MERGE_DTYPE = np.dtype([("kind", "<i4"), ("n_neighbors", "<i4"), ("n_add", "<i4"), ("reserved", "<i4"), ("rem_uid", "<u4", (2,)),
+                              ("rem_x", "<i4", (2,)), ("rem_y", "<i4", (2,)), ("add_x", "<i4", (2,)), ("add_y", "<i4", (2,)),
+                              ("add_size", "<f8", (2,)), ("add_ratio", "<f8", (2,)), ("add_angle", "<f8", (2,)), ("pos_delta", "<f8", (2,)),
+                              ("shape_delta", "<f8", (3,)), ("u", "<f8")], align=True)
+
 # every symbol include/mpp_b200.h declares
 SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_create", "mpp_ctx_destroy", "mpp_set_maps",
            "mpp_set_model", "mpp_set_kernels", "mpp_add_objects", "mpp_remove_objects", "mpp_clear_objects",
@@ -60,7 +65,7 @@ SYMBOLS = ["mpp_abi_version", "mpp_last_error", "mpp_abi_struct_size", "mpp_ctx_
            "mpp_query_neighbors", "mpp_copy_state", "mpp_pair_values", "mpp_run_chain", "mpp_sample_proposals",
            "mpp_proposal_probs", "mpp_combine", "mpp_run_windows", "mpp_ctx_reset", "mpp_run_window_rows", "mpp_window_grid",
            "mpp_set_window_trace", "mpp_window_stats", "mpp_run_windows_batch", "mpp_split_export", "mpp_split_attach",
-           "mpp_split_attach_local", "mpp_split_detach", "mpp_set_maps_band", "mpp_sample_points_2d"]
+           "mpp_split_attach_local", "mpp_split_detach", "mpp_set_maps_band", "mpp_sample_points_2d", "mpp_sample_split_merge", "mpp_split_merge_probs"]
 
 _lib = None
 
@@ -95,6 +100,8 @@ def load():
     lib.mpp_ctx_destroy.argtypes = [vp]
     lib.mpp_ctx_reset.argtypes = [vp, vp]
     lib.mpp_set_maps.argtypes = [vp, vp, vp, f64]
+    lib.mpp_sample_split_merge.argtypes = [vp, i32, f64, C.POINTER(f64), u64, u64, vp]
+    lib.mpp_split_merge_probs.argtypes = [vp, vp, f64, f64, f64, C.POINTER(f64), vp]
     lib.mpp_sample_points_2d.argtypes = [vp, i32, i32, i32, u64, vp, vp, i32, vp]
     lib.mpp_set_maps_band.argtypes = [vp, vp, vp, i32, i32, f64]
     lib.mpp_set_model.argtypes = [vp, C.POINTER(ModelParams)]
@@ -133,7 +140,7 @@ def load():
     if lib.mpp_abi_version() != 1:
         raise RuntimeError("libmpp_b200.so ABI version mismatch")
     sizes = [C.sizeof(ModelParams), C.sizeof(KernelParams), PROPOSAL_DTYPE.itemsize, STEP_RESULT_DTYPE.itemsize,
-             WINDOW_TRACE_DTYPE.itemsize]
+             WINDOW_TRACE_DTYPE.itemsize, SPLIT_MERGE_DTYPE.itemsize]
     for which, sz in enumerate(sizes):
         if lib.mpp_abi_struct_size(which) != sz:
             raise RuntimeError(f"ABI struct {which} size mismatch: C {lib.mpp_abi_struct_size(which)} vs python {sz}")

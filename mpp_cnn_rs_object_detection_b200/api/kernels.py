@@ -147,63 +147,80 @@ class DataDrivenShapeTransformKernel(DeviceKernel):  # transform_kernels.py:162-
 
 
 # ---------------------------------------------------------------------------------------------- optional split / merge
-class SplitSampler:  # split_and_merge_kernels.py:14-36
+class SplitSampler:  # split_and_merge_kernels.py:14-36 (parameters only: the draws and the density run on the device)
     def __init__(self, pos_radius: float, shape_sigmas: List[float], mappings):
-        self.pos_radius, self.shape_sigmas, self.mappings = pos_radius, shape_sigmas, mappings
+        self.pos_radius, self.shape_sigmas, self.mappings = float(pos_radius), [float(v) for v in shape_sigmas], mappings
         self.scaled_shaped_sigmas = [s * m.range for m, s in zip(mappings, shape_sigmas)]
         self.n_params = len(Rectangle.PARAMETERS)
 
-    def sample(self, rng: np.random.Generator):
-        pos = rng.uniform((0, 0), self.pos_radius)
-        while np.linalg.norm(pos) > self.pos_radius:
-            pos = rng.uniform((0, 0), self.pos_radius)
-        return pos, rng.normal((0,) * self.n_params, self.scaled_shaped_sigmas)
-
-    def pdf(self, pos_deltas, shape_deltas) -> float:
-        p_pos = 1 / (np.pi * self.pos_radius * self.pos_radius)
-        p_shape = [np.exp(-(d / s) ** 2 / 2) / (np.sqrt(2 * np.pi) * s) for d, s in zip(shape_deltas, self.scaled_shaped_sigmas)]
-        return float(p_pos * np.prod(p_shape))
-
 
 class _SplitMergeBase(Kernel):
-    """The optional two-object moves (use_split_merge=False in both shipped configurations).  Draws follow the reference's
-    numpy calls; neighbourhood counts come from the device index and the Delta-energy of the two-object perturbation from
-    the device (EnergyGraph._delta_multi).  They run through the step-by-step RJMCMC loop only."""
+    """The optional two-object moves (use_split_merge=False in both shipped configurations): device kernel ids 8 (split) and 9
+    (merge).  Draws (mpp_sample_split_merge: Philox seeded from the numpy Generator) and forward / backward densities
+    (mpp_split_merge_probs) run on the device; the Delta-energy of the two-object perturbation telescopes into single-object
+    Delta-energies on the device (EnergyGraph._delta_multi).  They run through the step-by-step RJMCMC loop only."""
+    KIND = -1
 
     def __init__(self, p_split: float, p_merge: float, split_sampler: SplitSampler, support_shape, intensity: float, merge_radius: float):
         self.p_split, self.p_merge, self.split_sampler = p_split, p_merge, split_sampler
         self.shape, self.intensity, self.radius = support_shape, intensity, merge_radius
         assert self.radius == self.split_sampler.pos_radius
 
+    def _engine(self, x: PointsSet):
+        st = x._state
+        st.use_kernels(self.intensity)
+        return st.engine
+
+    def _record(self, u: Perturbation) -> np.ndarray:
+        """The C-ABI form of a Perturbation of this kernel (what the densities need: the additions' positions, the shape deltas,
+        whether a second removal exists, the neighbour count)."""
+        rec = np.zeros(1, dtype=_lib.SPLIT_MERGE_DTYPE)
+        rec["kind"] = self.KIND
+        rec["rem_uid"][0] = (0xFFFFFFFF, 0xFFFFFFFF)
+        data = u.data or {}
+        rem = [] if u.removal is None else (list(u.removal) if isinstance(u.removal, (list, tuple)) else [u.removal])
+        add = [] if u.addition is None else (list(u.addition) if isinstance(u.addition, (list, tuple)) else [u.addition])
+        for k, q in enumerate(rem[:2]):
+            rec["rem_uid"][0][k] = 0  # present (the densities only look at presence)
+            rec["rem_x"][0][k], rec["rem_y"][0][k] = q.x, q.y
+        rec["n_add"] = len(add)
+        for k, a in enumerate(add[:2]):
+            rec["add_x"][0][k], rec["add_y"][0][k] = a.x, a.y
+            rec["add_size"][0][k], rec["add_ratio"][0][k], rec["add_angle"][0][k] = a.size, a.ratio, a.angle
+        rec["n_neighbors"] = int(data.get("n_neighbors", -1))
+        if self.KIND == 8 and "shape_delta" in data:
+            rec["pos_delta"][0][:] = np.asarray(data["pos_delta"], dtype=np.float64)
+            rec["shape_delta"][0][:] = np.asarray(data["shape_delta"], dtype=np.float64)
+        if self.KIND == 9 and len(rem) == 2:  # split_and_merge_kernels.py:170-172
+            rec["pos_delta"][0][:] = [(rem[0].x - rem[1].x) / 2, (rem[0].y - rem[1].y) / 2]
+            rec["shape_delta"][0][:] = [(getattr(rem[0], a) - getattr(rem[1], a)) / 2 for a in Rectangle.PARAMETERS]
+        return rec
+
+    def _probs(self, x: PointsSet, u: Perturbation):
+        assert u.type == self.__class__
+        return self._engine(x).split_merge_probs(self._record(u), self.p_split, self.p_merge, self.radius, self.split_sampler.shape_sigmas)
+
+    def forward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        return self._probs(x, u)[0]
+
+    def backward_probability(self, x: PointsSet, u: Perturbation) -> float:
+        return self._probs(x, u)[1]
+
+    def _draw(self, x: PointsSet, rng: np.random.Generator) -> np.ndarray:
+        return self._engine(x).sample_split_merge(self.KIND, self.radius, self.split_sampler.shape_sigmas, seed=int(rng.integers(0, 2 ** 62)))[0]
+
 
 class SplitKernel(_SplitMergeBase):  # split_and_merge_kernels.py:39-107
+    KIND = 8
+
     def sample_perturbation(self, x: PointsSet, rng: np.random.Generator) -> Perturbation:
         if len(x) == 0:
             return Perturbation(self.__class__)
-        p = x.random_choice(rng)
-        pos_delta, shape_delta = self.split_sampler.sample(rng)
-        new = []
-        for sgn in (-1, +1):
-            marks = {a: m.clip(getattr(p, a) + sgn * d) for a, d, m in zip(Rectangle.PARAMETERS, shape_delta, self.split_sampler.mappings)}
-            new.append(Rectangle(x=int(np.clip(p.x + sgn * pos_delta[0], 0, self.shape[0] - 1)),
-                                 y=int(np.clip(p.y + sgn * pos_delta[1], 0, self.shape[1] - 1)), **marks))
-        return Perturbation(self.__class__, addition=new, removal=p, data={"pos_delta": pos_delta, "shape_delta": shape_delta})
-
-    def forward_probability(self, x: PointsSet, u: Perturbation) -> float:
-        assert u.type == self.__class__
-        n = len(x)
-        if n == 0:
-            return self.p_kernel
-        return self.p_kernel * ((1 / n) * self.split_sampler.pdf(u.data["pos_delta"], u.data["shape_delta"])) / self.intensity
-
-    def backward_probability(self, x: PointsSet, u: Perturbation) -> float:
-        assert u.type == self.__class__
-        n = len(x) + 1
-        if n <= 1:
-            return self.p_merge
-        nb0 = len(x.get_potential_neighbors(u.addition[0], radius=self.radius)) + 1
-        nb1 = len(x.get_potential_neighbors(u.addition[1], radius=self.radius)) + 1
-        return self.p_merge * ((1 / n) * (1 / nb0) + (1 / n) * (1 / nb1))
+        r = self._draw(x, rng)
+        p = x._state.by_uid[int(r["rem_uid"][0])]
+        new = [Rectangle(x=int(r["add_x"][k]), y=int(r["add_y"][k]), size=float(r["add_size"][k]), ratio=float(r["add_ratio"][k]),
+                         angle=float(r["add_angle"][k])) for k in range(2)]
+        return Perturbation(self.__class__, addition=new, removal=p, data={"pos_delta": np.array(r["pos_delta"]), "shape_delta": np.array(r["shape_delta"])})
 
     @property
     def p_kernel(self) -> float:
@@ -211,36 +228,19 @@ class SplitKernel(_SplitMergeBase):  # split_and_merge_kernels.py:39-107
 
 
 class MergeKernel(_SplitMergeBase):  # split_and_merge_kernels.py:110-178
+    KIND = 9
+
     def sample_perturbation(self, x: PointsSet, rng: np.random.Generator) -> Perturbation:
         if len(x) <= 1:
             return Perturbation(self.__class__)
-        p0 = x.random_choice(rng)
-        neighbors = sorted(x.get_neighbors(p0, radius=self.radius), key=lambda q: (q.x, q.y, x._state.uid_of.get(q, 0)))
-        data = {"n_neighbors": len(neighbors)}
-        if not neighbors:
+        r = self._draw(x, rng)
+        data = {"n_neighbors": int(r["n_neighbors"])}
+        if int(r["n_add"]) == 0:
             return Perturbation(self.__class__, data=data)
-        p1 = neighbors[int(rng.integers(0, len(neighbors)))]
-        marks = {a: m.clip((getattr(p0, a) + getattr(p1, a)) / 2) for a, m in zip(Rectangle.PARAMETERS, self.split_sampler.mappings)}
-        p_new = Rectangle(x=int(np.clip((p0.x + p1.x) / 2, 0, self.shape[0] - 1)), y=int(np.clip((p0.y + p1.y) / 2, 0, self.shape[0] - 1)),
-                          **marks)  # the reference clips y with shape[0] too (split_and_merge_kernels.py:143)
+        p0, p1 = x._state.by_uid[int(r["rem_uid"][0])], x._state.by_uid[int(r["rem_uid"][1])]
+        p_new = Rectangle(x=int(r["add_x"][0]), y=int(r["add_y"][0]), size=float(r["add_size"][0]), ratio=float(r["add_ratio"][0]),
+                          angle=float(r["add_angle"][0]))
         return Perturbation(self.__class__, addition=p_new, removal=[p0, p1], data=data)
-
-    def forward_probability(self, x: PointsSet, u: Perturbation) -> float:
-        assert u.type == self.__class__
-        n = len(x)
-        if n <= 1 or u.data["n_neighbors"] == 0:
-            return self.p_kernel
-        return self.p_kernel * ((1 / n) * (1 / u.data["n_neighbors"]))
-
-    def backward_probability(self, x: PointsSet, u: Perturbation) -> float:
-        assert u.type == self.__class__
-        n = len(x) - 1
-        if n == 0 or u.removal is None:
-            return self.p_split
-        p0, p1 = u.removal[0], u.removal[1]
-        pos_delta = [(p0.x - p1.x) / 2, (p0.y - p1.y) / 2]
-        shape_delta = [(getattr(p0, a) - getattr(p1, a)) / 2 for a in Rectangle.PARAMETERS]
-        return self.p_split * ((1 / n) * self.split_sampler.pdf(pos_delta, shape_delta)) / self.intensity
 
     @property
     def p_kernel(self) -> float:

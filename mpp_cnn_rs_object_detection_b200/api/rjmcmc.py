@@ -253,6 +253,27 @@ def naive_detection(image_data: ImageWMaps, detection_threshold: float, energy_s
     return list(pts._state.objects())
 
 
+def plan_sweeps(shape, seed: int, budget: int, proposals_per_visit: int, sweep_offset: int = 0):
+    """(proposals per visit, number of sweeps, mean proposals per sweep) of the window sampler for a budget of `budget` RJMCMC
+    steps (max_iter + 1 of the reference's loop, stopping.py:42): counts the windows of every sweep's shifted grid (the host twin
+    of mpp_window_grid gives the offsets) instead of assuming the aligned grid, lowers the proposals per visit when one sweep at
+    the requested value would already exceed the budget, and stops at the first sweep that reaches it."""
+    from ..multi_gpu import grid_offset
+    h, w = int(shape[0]), int(shape[1])
+
+    def windows(s):
+        ox, oy = grid_offset(seed, sweep_offset + s)
+        return ((h + ox + 31) // 32) * ((w + oy + 31) // 32)
+
+    mean_windows = float(np.mean([windows(s) for s in range(16)]))
+    pv = int(max(1, min(proposals_per_visit, int(np.ceil(budget / mean_windows)))))
+    done, n = 0, 0
+    while done < budget:
+        done += windows(n) * pv
+        n += 1
+    return pv, n, done / n
+
+
 # ---------------------------------------------------------------------------------------------- sample_rjmcmc.py
 def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples: int, energy_combinator: EnergyCombinationModel,
                   init_config: Union[str, List[Rectangle], None], init_temperature: float, alpha_t: Union[float, str], burn_in: int,
@@ -312,16 +333,17 @@ def sample_rjmcmc(image_data: ImageWMaps, rng: np.random.Generator, num_samples:
         kernels[0]._kset.bind(points.points)
         st.use_combinator(energy_combinator)
         eng = st.engine
-        ncell = ((image_data.shape[0] + 31) // 32) * ((image_data.shape[1] + 31) // 32)
-        per_sweep = ncell * int(proposals_per_visit)
         stats = {"proposals": 0, "accepted": 0, "births": 0, "deaths": 0, "evaluated": 0, "sweeps": 0}
         seed = int(rng.integers(0, 2 ** 62))
+        # budget -> sweeps: a sweep visits every window of the shifted grid once ((H + ox + 31) // 32 x (W + oy + 31) // 32 of them,
+        # up to one row and one column more than the aligned grid), `proposals_per_visit` proposals each; on a small budget the
+        # proposals per visit are lowered so that one sweep does not exceed it
+        proposals_per_visit, total_sweeps, per_sweep = plan_sweeps(image_data.shape, seed, max_iter + 1, int(proposals_per_visit))
         # snapshot steps of the reference's sampling_rule, expressed in sweeps
         # num_samples == 1: the reference returns its last snapshot, at most samples_interval - 1 steps before the end of the
         # chain; the final state is returned here instead (no intermediate read-back)
         snap_steps = [s for s in range(burn_in, max_iter + 1) if s % samples_interval == 0] if (samples_interval > 0 and num_samples > 1) else []
-        snap_sweeps = sorted({-(-(s + 1) // per_sweep) for s in snap_steps})
-        total_sweeps = -(-(max_iter + 1) // per_sweep)
+        snap_sweeps = sorted({min(total_sweeps, max(1, int(np.ceil((s + 1) / per_sweep)))) for s in snap_steps})
         alpha_sweep = float(np.power(alpha_t, per_sweep))
         temp, done, states = float(init_temperature), 0, []
         for stop in snap_sweeps + ([total_sweeps] if (not snap_sweeps or snap_sweeps[-1] < total_sweeps) else []):
@@ -485,9 +507,8 @@ def sample_rjmcmc_tiles(images, rng: np.random.Generator, return_stats: bool = F
     totals = np.zeros(8, dtype=np.int64)
     n_launches = 0
     for shape, idx in by_shape.items():  # phase 2: one launch per shape
-        per_sweep = ((shape[0] + 31) // 32) * ((shape[1] + 31) // 32) * pv
-        n_sweeps = -(-(max_iter + 1) // per_sweep)
-        cnt = run_windows_batch([states[k]._state.engine for k in idx], [seeds[k] for k in idx], n_sweeps, pv, n_warps=nw, t0=float(t0),
+        pv_eff, n_sweeps, per_sweep = plan_sweeps(shape, seeds[idx[0]], max_iter + 1, pv)
+        cnt = run_windows_batch([states[k]._state.engine for k in idx], [seeds[k] for k in idx], n_sweeps, pv_eff, n_warps=nw, t0=float(t0),
                                 alpha_t=float(np.power(alpha_t, per_sweep)), t_target=float(t_target), grid_seed=seeds[idx[0]],
                                 read_counters=return_stats)
         n_launches += 1

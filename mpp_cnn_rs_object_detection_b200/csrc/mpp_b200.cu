@@ -16,6 +16,7 @@
 #include "mpp_chain.cuh"
 #include "mpp_sweep2.cuh"
 #include "mpp_multi.cuh"
+#include "mpp_split_merge.cuh"
 
 // ================================================================================================ host ctx
 struct mpp_ctx {
@@ -880,6 +881,7 @@ int mpp_abi_struct_size(int which) {
     case 2: return (int)sizeof(mpp_proposal);
     case 3: return (int)sizeof(mpp_step_result);
     case 4: return (int)sizeof(mpp_window_trace);
+    case 5: return (int)sizeof(mpp_split_merge);
     default: return -1;
     }
 }
@@ -1915,6 +1917,29 @@ extern "C" int mpp_sample_proposals(mpp_ctx *h, const int32_t *kernel_ids, int m
     const int blocks = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     DISPATCH(h, (k_sample_proposals<R><<<blocks, WARPS_PER_BLOCK * 32, 0, h->stream>>>(device_view<R>(h), h->d_rowcount, kernel_ids, m,
                                                                                     seed, offset, out)));
+    CUDA_TRY(cudaGetLastError());
+    return MPP_OK;
+}
+
+extern "C" int mpp_sample_split_merge(mpp_ctx *h, int kind, double radius, const double *sig, uint64_t seed, uint64_t offset, mpp_split_merge *out) {
+    NEED(h, h->model_set && h->kernels_set, "mpp_sample_split_merge: set the model and the kernels first");
+    if ((kind != 8 && kind != 9) || !(radius > 0.0) || radius > 32.0 || !sig || !out) return fail(MPP_ERR_INVALID, "mpp_sample_split_merge: bad arguments (radius <= 32)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = refresh_row_counts(h);
+    if (rc != MPP_OK) return rc;
+    DISPATCH(h, (k_sample_split_merge<R><<<1, 32, 0, h->stream>>>(device_view<R>(h), h->d_rowcount, kind, radius, sig[0], sig[1], sig[2], seed, offset, out)));
+    CUDA_TRY(cudaGetLastError());
+    return check_device_errors(h);
+}
+
+extern "C" int mpp_split_merge_probs(mpp_ctx *h, const mpp_split_merge *p, double p_split, double p_merge, double radius, const double *sig,
+                                     double *out) {
+    NEED(h, h->model_set && h->kernels_set, "mpp_split_merge_probs: set the model and the kernels first");
+    if (!p || !sig || !out || !(radius > 0.0) || radius > 32.0) return fail(MPP_ERR_INVALID, "mpp_split_merge_probs: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = refresh_row_counts(h);  // (recounts the objects: the densities use len(x))
+    if (rc != MPP_OK) return rc;
+    DISPATCH(h, (k_split_merge_probs<R><<<1, 32, 0, h->stream>>>(device_view<R>(h), p, p_split, p_merge, radius, sig[0], sig[1], sig[2], out)));
     CUDA_TRY(cudaGetLastError());
     return MPP_OK;
 }

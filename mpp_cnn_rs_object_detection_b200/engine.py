@@ -486,6 +486,25 @@ class Engine:
         self.launches += 1
         return out.cpu().numpy()
 
+    def sample_split_merge(self, kind: int, radius: float, shape_sigmas, seed: int = 0, offset: int = 0) -> np.ndarray:
+        """SplitKernel (kind 8) / MergeKernel (kind 9) .sample_perturbation on the device: one SPLIT_MERGE_DTYPE record."""
+        sig = (C.c_double * 3)(*[float(v) for v in shape_sigmas])
+        out = torch.zeros(_lib.SPLIT_MERGE_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mpp_sample_split_merge(self.ctx, int(kind), float(radius), sig, int(seed), int(offset), out.data_ptr()))
+        self.launches += 2
+        return out.cpu().numpy().view(_lib.SPLIT_MERGE_DTYPE).reshape(1).copy()
+
+    def split_merge_probs(self, record: np.ndarray, p_split: float, p_merge: float, radius: float, shape_sigmas):
+        """(forward, backward) densities of one split / merge perturbation against the current state, on the device."""
+        rec = np.ascontiguousarray(record, dtype=_lib.SPLIT_MERGE_DTYPE).reshape(1)
+        d = torch.as_tensor(rec.view(np.uint8).reshape(-1)).to(self.device)
+        sig = (C.c_double * 3)(*[float(v) for v in shape_sigmas])
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mpp_split_merge_probs(self.ctx, d.data_ptr(), float(p_split), float(p_merge), float(radius), sig, out.data_ptr()))
+        self.launches += 2
+        v = out.cpu().numpy()
+        return float(v[0]), float(v[1])
+
     def sample_births(self, n: int, seed: int = 0) -> np.ndarray:
         out = torch.empty((n, 5), dtype=torch.int32, device=self.device)
         _lib.check(self.lib.mpp_sample_births(self.ctx, int(n), int(seed), out.data_ptr()))

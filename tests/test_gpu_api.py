@@ -528,3 +528,50 @@ def test_rjmcmc_timer_interface():
         assert key in t.timings and len(t.timings[key]) == 41, (key, len(t.timings.get(key, [])))
     assert all(v >= 0 for v in t.timings["total"]) and len(chain.get_state_log()) >= 1
     t.show_results()
+
+
+def test_split_merge_device_draws():
+    """Device draws of the split / merge kernels (mpp_sample_split_merge): structure of the perturbation, support of the
+    deltas, uniform choice among the neighbours within the radius, and fwd / bwd consistency of a split with the merge that undoes it."""
+    api = _api()
+    g = gu.load("split_merge_legacy.npz")
+    _, det, marks = gu.scene_inputs(g)
+    setup, comb = _setup(api, "legacy")
+    img = _image(api, det, marks)
+    unit, pair = setup.make_energies(img)
+    rects = [api.Rectangle(int(r[0]), int(r[1]), r[2], r[3], r[4]) for r in g["config"]]
+    eps = api.EPointsSet(rects, det.shape, unit, pair)
+    kernels, p = api.make_kernels(img, intensity=float(len(rects)), rng=np.random.default_rng(0), use_split_merge=True)
+    split, merge = kernels[8], kernels[9]
+    rng = np.random.default_rng(5)
+    sig = [0.1 * 32.0, 0.1 * 1.0, 0.1 * np.pi]
+    deltas = []
+    for _ in range(300):
+        u = split.sample_perturbation(eps.points, rng)
+        q, (a0, a1) = u.removal, u.addition
+        assert q in rects and len(u.addition) == 2
+        d, sd = u.data["pos_delta"], u.data["shape_delta"]
+        assert d[0] >= 0 and d[1] >= 0 and np.hypot(*d) <= 16 + 1e-9          # quarter disc (the reference draws uniform(0, r))
+        assert a0.x == int(np.clip(q.x - d[0], 0, det.shape[0] - 1)) and a1.y == int(np.clip(q.y + d[1], 0, det.shape[1] - 1))
+        assert abs(a1.size - np.clip(q.size + sd[0], 0, 32)) < 1e-6 and abs(a0.ratio - np.clip(q.ratio - sd[1], 0, 1)) < 1e-6
+        assert 0 <= a0.angle < np.pi + 1e-9 and abs((a1.angle - (q.angle + sd[2])) % np.pi) < 1e-6 or abs((a1.angle - (q.angle + sd[2])) % np.pi - np.pi) < 1e-6
+        f, b = split.forward_probability(eps.points, u), split.backward_probability(eps.points, u)
+        assert f > 0 and b > 0
+        deltas.append(np.concatenate([d, sd / np.array(sig)]))
+    deltas = np.array(deltas)
+    assert abs(deltas[:, 2:].mean()) < 0.15 and 0.8 < deltas[:, 2:].std() < 1.2   # standard normal shape deltas
+    picks = {}
+    for _ in range(400):
+        u = merge.sample_perturbation(eps.points, rng)
+        nn = u.data["n_neighbors"]
+        if u.removal is None:
+            assert nn == 0 and u.addition is None
+            continue
+        p0, p1 = u.removal
+        assert p0 is not p1 and np.hypot(p0.x - p1.x, p0.y - p1.y) <= 16
+        assert nn == len(eps.points.get_neighbors(p0, radius=16))
+        assert u.addition.x == int(np.clip((p0.x + p1.x) / 2, 0, det.shape[0] - 1)) and abs(u.addition.size - (p0.size + p1.size) / 2) < 1e-6
+        picks.setdefault(id(p0), {}).setdefault(id(p1), 0)
+        picks[id(p0)][id(p1)] += 1
+        assert merge.forward_probability(eps.points, u) == pytest.approx(p[9] / len(rects) / nn, rel=1e-12)
+    assert any(len(v) > 1 for v in picks.values())   # objects with several neighbours see more than one of them drawn
