@@ -48,6 +48,8 @@ struct WinState {
     R dm0[W2_K], dm1[W2_K], dm2[W2_K];                  // per-mark energies (window objects; legacy: before the mean)
     float detv[W2_K], pn0[W2_K], pn1[W2_K], pn2[W2_K];  // det value and normalised mark probabilities (window objects)
     R ov1[W2_K], ov2[W2_K], al1[W2_K], al2[W2_K];
+    R fcur[W2_K];          // current combined energy f(unit terms, ov1, al1) of every entry whose reductions are maintained (W2_INNER):
+                           // the "before" half of every Delta-energy, kept up to date by the commits instead of being recomputed
     short aov[W2_K], aal[W2_K], aov2[W2_K], aal2[W2_K];  // staged indices of the best / second-best partners
     unsigned char flags[W2_K];
     uint32_t order[W2_K];  // staging scratch: handles in canonical order
@@ -217,7 +219,7 @@ __device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w,
                     if (d2 <= m.al_d2) { al = align_magnitude(geo_w(w, k), ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
                 }
             }
-            if (touched) acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, ov_b, al_b);
+            if (touched) acc += f_obj(m, w, k, ov_a, al_a) - w.fcur[k];
         }
         if (has_add) { po[k] = o; pa[k] = al; }
     }
@@ -232,7 +234,7 @@ __device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w,
         t.ratio = r_abs((R)m.f_target_ratio - a.ratio);
         acc += combine_fast(m, t);
     }
-    if (r >= 0) acc -= f_obj(m, w, r, w.ov1[r], w.al1[r]);
+    if (r >= 0) acc -= w.fcur[r];
     return acc;
 }
 
@@ -619,6 +621,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         // (Most accepted moves are mark transforms that leave the alignment value with every neighbour as it was.)
         bool redo_ov = r >= 0 && (w.aov[k] == r || w.aov2[k] == r), redo_al = r >= 0 && (w.aal[k] == r || w.aal2[k] == r);
         const bool was_ov = redo_ov && s == r, was_al = redo_al && s == r;  // r held a place in this entry's top-2 and is being replaced
+        const R o1_old = w.ov1[k], a1_old = w.al1[k];
         const R o = s >= 0 ? po[k] : (R)0, al = s >= 0 ? pa[k] : (R)0;
         if (s >= 0 && s == r && (w.flags[k] & W2_INNER)) {
             if (redo_ov) {
@@ -656,9 +659,13 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
             }
         }
         if ((redo_ov || redo_al) && (w.flags[k] & W2_INNER)) recompute_top2(m, w, k, redo_ov, redo_al, sx, sy);
+        if ((w.flags[k] & W2_INNER) && (w.ov1[k] != o1_old || w.al1[k] != a1_old)) w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]);
     }
     if (s >= 0 && !__any_sync(MPP_FULL, any_pair)) {  // no partner within reach of the new object
-        if (lane == 0) { w.ov1[s] = 0; w.ov2[s] = 0; w.al1[s] = 0; w.al2[s] = 0; w.aov[s] = -1; w.aov2[s] = -1; w.aal[s] = -1; w.aal2[s] = -1; }
+        if (lane == 0) {
+            w.ov1[s] = 0; w.ov2[s] = 0; w.al1[s] = 0; w.al2[s] = 0; w.aov[s] = -1; w.aov2[s] = -1; w.aal[s] = -1; w.aal2[s] = -1;
+            w.fcur[s] = f_obj(m, w, s, (R)0, (R)0);
+        }
         __syncwarp();
         return;
     }
@@ -680,6 +687,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         if (lane == 0) {
             w.ov1[s] = mo; w.ov2[s] = so; w.aov[s] = (short)(mo > (R)0 ? ao : -1); w.aov2[s] = (short)(so > (R)0 ? ao2 : -1);
             w.al1[s] = ma; w.al2[s] = sa2; w.aal[s] = (short)(ma > (R)0 ? aa : -1); w.aal2[s] = (short)(sa2 > (R)0 ? aa2 : -1);
+            w.fcur[s] = f_obj(m, w, s, mo, ma);
         }
     }
     __syncwarp();
@@ -1141,7 +1149,7 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
             R ov_a = w.ov1[k], al_a = w.al1[k];
             if (d2 <= m.ov_d2) { const R o = pair_ov_w(m, w, k, ga, rad_a, d2, sx, sy); ov_a = r_max(ov_a, o); ov_add = r_max(ov_add, o); }
             if (d2 <= m.al_d2) { const R al = align_magnitude(geo_w(w, k), ga, m.rewarding); al_a = r_max(al_a, al); al_add = r_max(al_add, al); }
-            acc += f_obj(m, w, k, ov_a, al_a) - f_obj(m, w, k, w.ov1[k], w.al1[k]);
+            acc += f_obj(m, w, k, ov_a, al_a) - w.fcur[k];
         }
     }
     for (int off = G >> 1; off > 0; off >>= 1) {
@@ -1365,7 +1373,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
             w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
         }
-        if (w.flags[k] & W2_INNER) recompute_top2(m, w, k, true, true, sx, sy);
+        if (w.flags[k] & W2_INNER) { recompute_top2(m, w, k, true, true, sx, sy); w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]); }
     }
     }  // stager
     __syncthreads();
