@@ -48,6 +48,7 @@ struct WinState {
     R dm0[W2_K], dm1[W2_K], dm2[W2_K];                  // per-mark energies (window objects; legacy: before the mean)
     float detv[W2_K], pn0[W2_K], pn1[W2_K], pn2[W2_K];  // det value and normalised mark probabilities (window objects)
     R ov1[W2_K], ov2[W2_K], al1[W2_K], al2[W2_K];
+    R fa[W2_K], fg[W2_K];  // the combinator's gated linear form per entry: f = fa + fg * (c_ov * ov + c_al * al) (+ logistic)
     R fcur[W2_K];          // current combined energy f(unit terms, ov1, al1) of every entry whose reductions are maintained (W2_INNER):
                            // the "before" half of every Delta-energy, kept up to date by the commits instead of being recomputed
     short aov[W2_K], aal[W2_K], aov2[W2_K], aal2[W2_K];  // staged indices of the best / second-best partners
@@ -178,14 +179,19 @@ __device__ __noinline__ void recompute_top2(const ModelDev &m, WinState<R> &w, i
 #else
 #define MPP_DELTA_INL
 #endif
+// unit part of the combinator's gated linear form (combine_fast) for staged entry k: everything but the two partner terms
+template <typename R>
+__device__ __forceinline__ void unit_form(const ModelDev &m, WinState<R> &w, int k) {
+    const R uin = (R)m.c_m0 * w.tm0[k] + (R)m.c_m1 * w.tm1[k] + (R)m.c_m2 * w.tm2[k] + (R)m.c_area * area_prior_fast<R>(m, w.hl[k], w.hw[k]) +
+                  (R)m.c_ratio * r_abs((R)m.f_target_ratio - w.ratio[k]);
+    const R g = (m.gate && !(w.pos[k] <= (R)m.gate_thr)) ? (R)0 : (R)1;
+    w.fa[k] = (R)m.c_pos * w.pos[k] + g * uin + (R)m.c_0;
+    w.fg[k] = g;
+}
 template <typename R>
 __device__ MPP_FOBJ_INL R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
-    Terms<R> t;
-    t.pos = w.pos[k]; t.m0 = w.tm0[k]; t.m1 = w.tm1[k]; t.m2 = w.tm2[k];
-    t.ov = ov; t.al = (m.rewarding ? (R)-1 : (R)1) * al;
-    t.area = area_prior_fast<R>(m, w.hl[k], w.hw[k]);
-    t.ratio = r_abs((R)m.f_target_ratio - w.ratio[k]);
-    return combine_fast(m, t);
+    const R e = w.fa[k] + w.fg[k] * ((R)m.c_ov * ov + (R)m.c_al * ((m.rewarding ? (R)-1 : (R)1) * al));
+    return m.logistic ? (R)2 / ((R)1 + r_exp(-e)) - (R)1 : e;
 }
 
 // Delta-energy of removing staged entry r (r < 0: none) and/or adding `a` (has_add), from the staged state only.
@@ -378,7 +384,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     const int wx = w.x1 - w.x0, wy = w.y1 - w.y0;
     int r = -1;
     if (kernel != 0 && kernel != 2) {
-        r = pick_window_object(w, min(nc - 1, (int)(u01f(q0.y) * (float)nc)), lane);
+        r = w.winlist[min(nc - 1, (int)(u01f(q0.y) * (float)nc))];  // staged indices of the alive window objects, ascending
         if (r < 0) return;  // cannot happen (nc > 0)
     }
     e->r = r;
@@ -561,6 +567,8 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
 // Applies an accepted proposal to the staged state and writes the new record (executed by the warp that evaluated it:
 // its po / pa scratch still holds the pair values between every staged entry and the added object).  The occupancy
 // masks of the window's storage cells are only published at the end of the visit.
+template <typename R> __device__ __forceinline__ void rebuild_winlist(WinState<R> &w, int lane);
+
 template <typename R, bool SPLIT = false>
 __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy, const R *po, const R *pa) {
     const ModelDev &m = c.m;
@@ -597,6 +605,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
             shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &w.tm0[s], &w.tm1[s], &w.tm2[s]);
             w.detv[s] = a.detv; w.pn0[s] = a.pn0; w.pn1[s] = a.pn1; w.pn2[s] = a.pn2;
             w.flags[s] = W2_ALIVE | W2_WIN | W2_INNER;
+            unit_form(m, w, s);
             w.n_win += 1; w.dn += 1; w.masks_dirty = 1;
             Rec<R> rec;
             rec.x = a.x; rec.y = a.y; rec.cls = a.cls; rec.uid = w.uid[s];
@@ -608,6 +617,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         }
     }
     __syncwarp();
+    if ((r >= 0) != (s >= 0)) rebuild_winlist(w, lane);  // a birth or a death changes the list the proposals pick from
     // reductions: incremental for the addition (pair values are in po / pa); entries whose best partner was the
     // removed object are rescanned; the new object's own top-2 is the top-2 of po / pa
     const int n = w.n;
@@ -1360,10 +1370,12 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa; w.rad[p] = r_sqrt(rec.hl * rec.hl + rec.hw * rec.hw);
         w.pos[p] = rec.e_pos; w.tm0[p] = rec.e_m[0]; w.tm1[p] = rec.e_m[1]; w.tm2[p] = rec.e_m[2];
         w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
+        unit_form(m, w, p);
         if (inw) atomicAdd(&w.n_win, 1);
     }
     stage_sync(sg);
     MPP_MARK(3);
+    if (warp == 0) rebuild_winlist(w, lane);
     // phase D: per-mark details of the window objects (deaths, translations, mark transforms): seven gathers per object;
     // phase E: partner reductions of everything a move in the window can affect; one thread per object for both
     for (int k = sidx; k < n0; k += sg) {
