@@ -289,7 +289,9 @@ int mpp_run_sweeps(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int stri
  * schedule 0: one launch per colour class (9 per sweep, a device-wide barrier between colours).  schedule 1: one
  * persistent kernel for the whole call; window visits are claimed in (sweep, colour, window) order and each starts as soon
  * as the earlier visits within 64 px of it have completed (dataflow; same chain as schedule 0, bit for bit).
- * counters_host as in mpp_run_sweeps. */
+ * counters_host as in mpp_run_sweeps.  Objects born in sweep s get the uid 0x80000000 | ((s * (nx + 2) * (ny + 2) + window) * 128 +
+ * proposal index); calls whose sweep numbers would take that product beyond 2^31 are refused (MPP_ERR_INVALID): restart
+ * the numbering (sweep_offset) with another seed. */
 int mpp_run_windows(mpp_ctx *ctx, int n_sweeps, int proposals_per_visit, int n_warps, int schedule, double t0,
                     double alpha_t, double t_target, uint64_t seed, uint64_t sweep_offset,
                     unsigned long long *counters_host, float *debug_maxdiff);

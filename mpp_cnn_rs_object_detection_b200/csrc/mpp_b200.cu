@@ -64,6 +64,12 @@ struct mpp_ctx {
 };
 
 #define MPP_MAX_DEVICES 64
+#ifdef MPP_TRACE
+#define MPP_KSTATS_COPY 64   // instrumented build: entries 40.. hold per-kernel evaluation timers (tools/visit_timers.py)
+#else
+#define MPP_KSTATS_COPY MPP_WINDOW_STATS
+#endif
+#define MPP_KSTATS_ALLOC 64
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
 
@@ -909,8 +915,8 @@ int mpp_ctx_create(mpp_ctx **out, int device, int height, int width, int precisi
     CUDA_TRY(cudaMalloc(&h->d_next_uid, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_err, sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
-    CUDA_TRY(cudaMalloc(&h->d_kstats, sizeof(unsigned long long) * MPP_WINDOW_STATS));
-    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
+    CUDA_TRY(cudaMalloc(&h->d_kstats, sizeof(unsigned long long) * MPP_KSTATS_ALLOC));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_KSTATS_ALLOC, h->stream));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, 128));
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMemsetAsync(h->d_mask, 0, sizeof(uint32_t) * h->ncell, h->stream));
@@ -959,7 +965,7 @@ int mpp_ctx_reset(mpp_ctx *h, void *stream) {
     CUDA_TRY(cudaMemsetAsync(h->d_next_uid, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_KSTATS_ALLOC, h->stream));
     h->det = nullptr; h->marks = nullptr; h->det_sum = 0.f; h->map_row0 = 0; h->map_rows = 0;
     h->maps_set = false; h->model_set = false; h->kernels_set = false;
     h->window_uid_next = 0x80000000u;
@@ -1420,6 +1426,15 @@ static uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
+// uids of objects born in sweep s are 0x80000000 | ((s * cells + window) * 128 + proposal index): unique while the product stays
+// below 2^31.  A call whose last sweep would exceed that is refused (two live objects could otherwise share a uid and the
+// host mirror, which names objects by uid, would merge them).
+static bool uid_space_ok(const mpp_ctx *h, uint64_t sweep_offset, int n_sweeps) {
+    const uint64_t cells = (uint64_t)(h->nx + 2) * (uint64_t)(h->ny + 2);
+    return (sweep_offset + (uint64_t)std::max(n_sweeps, 0)) * cells * (uint64_t)W2_PRE < 0x80000000ull;
+}
+#define UID_SPACE_MSG "sweep numbers beyond 2^31 / (128 * window count): the uids of born objects would wrap; restart the sweep numbering (sweep_offset) with another seed"
+
 template <typename R, int NW, bool DBG, bool SIMT = false>
 static cudaError_t launch_sweep2(mpp_ctx *h, int ci, int cj, int n_wi, int n_wj, int ox, int oy, int per_visit, float temp, uint64_t seed,
                                  uint64_t sweep_id, float *dbg) {
@@ -1517,6 +1532,7 @@ extern "C" int mpp_run_windows(mpp_ctx *h, int n_sweeps, int per_visit, int n_wa
     if (schedule != 0 && schedule != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows: schedule must be 0 (colour barriers) or 1 (dataflow)");
     if (h->m.setup == MPP_SETUP_TOY) return fail(MPP_ERR_STATE, "mpp_run_windows: needs a map-driven energy model");
     if (h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_windows: the window sampler is float32 only (use mpp_run_chain / mpp_replay for float64)");
+    if (!uid_space_ok(h, sweep_offset, n_sweeps)) return fail(MPP_ERR_INVALID, "mpp_run_windows: " UID_SPACE_MSG);
     CUDA_TRY(cudaSetDevice(h->device));
     // `alpha_t` is the temperature factor of one sweep; inside a visit the i-th proposal of every window stands for step
     // i * (number of windows) of the sweep, so the temperature decays by alpha_t^(1/per_visit) per proposal index and the
@@ -1581,6 +1597,7 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
         return fail(MPP_ERR_INVALID, "mpp_run_window_rows: bad arguments");
     if (n_warps != 0 && n_warps != 1 && n_warps != 2 && n_warps != 4 && n_warps != 8) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: n_warps must be 0, 1, 2, 4 or 8");
     if (h->m.setup == MPP_SETUP_TOY || h->precision != MPP_PRECISION_FP32) return fail(MPP_ERR_STATE, "mpp_run_window_rows: float32 map-driven model only");
+    if (!uid_space_ok(h, sweep_id, 1)) return fail(MPP_ERR_INVALID, "mpp_run_window_rows: " UID_SPACE_MSG);
     CUDA_TRY(cudaSetDevice(h->device));
     h->visit_alpha = 1.f; h->visit_tfloor = 0.f;  // one temperature per phase
     const uint64_t hsh = splitmix64(seed ^ splitmix64(sweep_id));
@@ -1612,11 +1629,11 @@ extern "C" int mpp_run_window_rows(mpp_ctx *h, int per_visit, int n_warps, doubl
 extern "C" int mpp_window_stats(mpp_ctx *h, unsigned long long *out_host) {
     if (!h || !out_host) return fail(MPP_ERR_INVALID, "mpp_window_stats: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<unsigned long long> tmp(MPP_WINDOW_STATS);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_kstats, sizeof(unsigned long long) * MPP_WINDOW_STATS, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_WINDOW_STATS, h->stream));
+    std::vector<unsigned long long> tmp(MPP_KSTATS_ALLOC);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_kstats, sizeof(unsigned long long) * MPP_KSTATS_ALLOC, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_kstats, 0, sizeof(unsigned long long) * MPP_KSTATS_ALLOC, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < MPP_WINDOW_STATS; ++i) out_host[i] = tmp[i];
+    for (int i = 0; i < MPP_KSTATS_COPY; ++i) out_host[i] = tmp[i];
     return MPP_OK;
 }
 
@@ -1749,6 +1766,7 @@ extern "C" int mpp_run_windows_batch(mpp_ctx **ctxs, const uint64_t *seeds, int 
             return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: scenes must share shape and device, float32 map-driven models only");
         if (h->split && n_scenes != 1) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: a split scene runs alone on its rank");
     }
+    if (!uid_space_ok(h0, sweep_offset, n_sweeps)) return fail(MPP_ERR_INVALID, "mpp_run_windows_batch: " UID_SPACE_MSG);
     CUDA_TRY(cudaSetDevice(h0->device));
     for (int k = 0; k < n_scenes; ++k) {
         mpp_ctx *h = ctxs[k];

@@ -373,6 +373,9 @@ template <typename R, bool DBG>
 __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_t seed, uint32_t win_id, uint64_t sweep_id, int it,
                                   float temp, int lane, R *sx, R *sy, R *po, R *pa, Eval<R> *e, float *dbg_maxdiff, mpp_window_trace *tr) {
     // random words and kernel of proposal `it`: drawn ahead by predraw_births (same counter-based stream)
+#ifdef MPP_TRACE
+    const long long t_e0 = clock64();
+#endif
     const uint4 q0 = make_uint4(w.pq[0][it], w.pq[1][it], w.pq[2][it], w.pq[3][it]);
     const uint4 q1 = make_uint4(w.pq[4][it], w.pq[5][it], w.pq[6][it], w.pq[7][it]);
     const ModelDev &m = c.m;
@@ -548,7 +551,18 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             return;
         }
     }
+#ifdef MPP_TRACE
+    const long long t_d0 = clock64();
+#endif
     const R de = delta_staged(m, w, r, e->has_add, a, lane, sx, sy, po, pa);
+#ifdef MPP_TRACE
+    if (lane == 0) {
+        const long long t_d1 = clock64();
+        atomicAdd(c.kstats + 40 + kernel, (unsigned long long)(t_d0 - t_e0));   // draw part of this kernel
+        atomicAdd(c.kstats + 48 + kernel, (unsigned long long)(t_d1 - t_d0));   // Delta-energy part
+        atomicAdd(c.kstats + 56 + kernel, 1ull);
+    }
+#endif
 #ifndef MPP_TRACE
     if (DBG && dbg_maxdiff) {
         const R db = delta_brute(m, w, r, e->has_add, a, lane, sx, sy);
@@ -1285,9 +1299,10 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
             w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
             w.dn = 0; w.n_acc = 0; w.n_birth = 0; w.n_death = 0; w.n_eval = 0; w.n_done = 0; w.masks_dirty = 0;
-            // uids of objects born here: a function of (sweep, window) only, so that the chain and the uids do not depend on
-            // the schedule or on how a scene is split across GPUs (wraps after 2^31 / (windows * per_visit) sweeps)
-            w.uid_base = 0x80000000u | (uint32_t)(((sweep_id * (uint64_t)((c.nx + 2) * (c.ny + 2)) + (uint64_t)(wi * (c.ny + 2) + wj)) * (uint64_t)per_visit) & 0x7fffffffull);
+            // uids of objects born here: a function of (sweep, window, proposal index) only, so that the chain and the uids do not
+            // depend on the schedule, on the proposals per visit of other calls, or on how a scene is split across GPUs.  The
+            // host refuses sweep numbers whose uids would leave the 31-bit range (uid_space_ok in mpp_b200.cu).
+            w.uid_base = 0x80000000u | (uint32_t)(((sweep_id * (uint64_t)((c.nx + 2) * (c.ny + 2)) + (uint64_t)(wi * (c.ny + 2) + wj)) * (uint64_t)W2_PRE) & 0x7fffffffull);
             for (int q = 0; q < 4; ++q) {
                 const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
                 const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);

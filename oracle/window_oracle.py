@@ -235,7 +235,7 @@ class WindowOracle:
         near = [o for o in self.state if x0 - 64 <= o.x < x1 + 64 and y0 - 64 <= o.y < y1 + 64]
         slots: List[Optional[WRect]] = sorted(near, key=lambda o: (o.x * 16384 + o.y, o.uid))
         in_win = lambda o: o is not None and x0 <= o.x < x1 and y0 <= o.y < y1  # noqa: E731
-        uid_base = 0x80000000 | (((sweep * (self.nx + 2) * (self.ny + 2) + wi * (self.ny + 2) + wj) * pv) & 0x7fffffff)
+        uid_base = 0x80000000 | (((sweep * (self.nx + 2) * (self.ny + 2) + wi * (self.ny + 2) + wj) * 128) & 0x7fffffff)
         row_mass = self.rowcum[x0:x1, y1] - self.rowcum[x0:x1, y0]
         win_mass = float(row_mass.sum())
         lam_unif = self.intensity * (wx * wy) / float(H * W)

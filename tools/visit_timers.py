@@ -41,3 +41,12 @@ for nw, pv in ((8, 96),):
                       ("rounds", 8), ("acc", 9), ("total us", 10), ("evaluated", 11)):
         v = tr[:, col] / 1900.0 if "us" in name else tr[:, col]
         print(f"  {name:12s} mean {v.mean():8.2f}  p50 {np.median(v):8.2f}  p90 {np.percentile(v, 90):8.2f}  max {v.max():8.2f}")
+
+    raw = (C.c_ulonglong * 64)()
+    _lib.check(eng.lib.mpp_window_stats(eng.ctx, raw))
+    v = [int(x) for x in raw]
+    names = ["uniform_birth", "uniform_death", "data_birth", "data_death", "gaussian_translation", "data_translation", "gaussian_transform", "data_transform"]
+    print("  per-kernel evaluation time of the generic rounds (us, instrumented build): draw part | Delta-energy part | count")
+    for k in range(8):
+        if v[56 + k]:
+            print(f"    {names[k]:22s} {v[40 + k] / v[56 + k] / 1900:6.2f} | {v[48 + k] / v[56 + k] / 1900:6.2f} | {v[56 + k]}")
