@@ -90,6 +90,13 @@ def n_rect_for(args):
     return args.n_rect or int(round(2600 * (args.size * args.size) / (2048.0 * 2048.0)))
 
 
+def workload_config(args):
+    """The `config` object of BOTH arms (identical by construction, so that the driver's same-config check holds): what the
+    workload is; how a run went is reported under `run`."""
+    return {"workload": workload_name(args), "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated",
+            "l2": "inputs larger than L2 (mark maps 3 x %.0f MB per scene)" % (args.size * args.size * 32 * 4 / 1e6)}
+
+
 def workload_name(args):
     return (f"synthetic {args.size}x{args.size} scene, {n_rect_for(args)} candidate rectangles (make_synth recipe), "
             f"hrcM energies, fixed T={args.temperature}")
@@ -284,7 +291,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "decomposition": "256x256 patches, one sequential chain per host core"},
+            "config": workload_config(args), "run": {"decomposition": "256x256 patches, one sequential chain per host core"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port", "sample": sample},
             "ms_per_image": image["ms_per_image"], "whole_image": image, "single_chain": single,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -698,12 +705,12 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sampler": args.sampler, "sweeps_per_step": args.sweeps,
-                       "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "schedule": args.schedule if args.sampler == "windows" else "colours", "colour_stride": 3 if args.sampler == "windows" else args.stride,
-                       "attempted_per_step": attempted / args.steps,
-                       "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated (empty perturbations and moves leaving their window are not counted)", "objects_start": n0, "objects_end": n1, "acceptance": acc,
-                       "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU",
-                       "l2": "inputs larger than L2 (mark maps 3 x %.0f MB)" % (h * w * 32 * 4 / 1e6)},
+            "config": workload_config(args),
+            "run": {"sampler": args.sampler, "sweeps_per_step": args.sweeps,
+                    "proposals_per_visit": args.per_visit, "warps_per_window": args.warps, "schedule": args.schedule if args.sampler == "windows" else "colours", "colour_stride": 3 if args.sampler == "windows" else args.stride,
+                    "attempted_per_step": attempted / args.steps,
+                    "proposal_definition": "RJMCMC steps whose Delta-energy was evaluated (empty perturbations and moves leaving their window are not counted)", "objects_start": n0, "objects_end": n1, "acceptance": acc,
+                    "proposals_per_step": proposals / args.steps, "parallelism": f"{world} independent scene(s), one per GPU"},
             "ms_per_image": ms / args.steps, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline,
             "proposal_mix": mix}
 

@@ -1326,30 +1326,31 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
         const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
         int n = 0;
-        for (int b = 0; b < ncells; b += 32) {
-            const int k = b + lane;
-            int cell = 0;
-            uint32_t msk = 0;
-            if (k < ncells) { cell = (sy0 + k % ncw) + (sx0 + k / ncw) * c.ny; msk = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell)); }
-            uint32_t any = __ballot_sync(MPP_FULL, msk != 0);
-            while (any) {
-                uint32_t h = 0;
-                int4 head = make_int4(0, 0, 0, 0);
-                bool keep = false;
-                if (msk) {
-                    const int slot = __ffs(msk) - 1;
-                    msk &= msk - 1;
-                    h = (uint32_t)cell * 32u + slot;
-                    head = ld_state<SPLIT>(reinterpret_cast<const int4 *>(rec_ptr<SPLIT>(c, h)));
-                    keep = head.x >= x0 - 64 && head.x < x1 + 64 && head.y >= y0 - 64 && head.y < y1 + 64;
-                }
+        // the occupancy masks of the (at most 36) storage cells in one round trip, then the 16-byte record heads two per lane
+        // and round trip (the order in which entries are collected does not matter: phase B sorts them)
+        int cell0 = 0, cell1 = 0;
+        uint32_t msk0 = 0, msk1 = 0;
+        if (lane < ncells) { cell0 = (sy0 + lane % ncw) + (sx0 + lane / ncw) * c.ny; msk0 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell0)); }
+        if (lane + 32 < ncells) { cell1 = (sy0 + (lane + 32) % ncw) + (sx0 + (lane + 32) / ncw) * c.ny; msk1 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell1)); }
+        while (__any_sync(MPP_FULL, (msk0 | msk1) != 0)) {
+            uint32_t h[2] = {0, 0};
+            int4 head[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+            bool have[2] = {false, false};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (msk0) { const int slot = __ffs(msk0) - 1; msk0 &= msk0 - 1; h[q] = (uint32_t)cell0 * 32u + slot; have[q] = true; }
+                else if (msk1) { const int slot = __ffs(msk1) - 1; msk1 &= msk1 - 1; h[q] = (uint32_t)cell1 * 32u + slot; have[q] = true; }
+                if (have[q]) head[q] = ld_state<SPLIT>(reinterpret_cast<const int4 *>(rec_ptr<SPLIT>(c, h[q])));
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const bool keep = have[q] && head[q].x >= x0 - 64 && head[q].x < x1 + 64 && head[q].y >= y0 - 64 && head[q].y < y1 + 64;
                 const uint32_t kb = __ballot_sync(MPP_FULL, keep);
                 if (keep) {
                     const int p = n + __popc(kb & ((1u << lane) - 1));
-                    if (p < W2_K) { w.handle[p] = h; w.x[p] = head.x * 16384 + head.y; w.uid[p] = (uint32_t)head.w; }
+                    if (p < W2_K) { w.handle[p] = h[q]; w.x[p] = head[q].x * 16384 + head[q].y; w.uid[p] = (uint32_t)head[q].w; }
                 }
                 n += __popc(kb);
-                any = __ballot_sync(MPP_FULL, msk != 0);
             }
         }
         if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
