@@ -167,6 +167,50 @@ __device__ __noinline__ void recompute_top2(const ModelDev &m, WinState<R> &w, i
     if (do_al) { w.al1[k] = a1; w.al2[k] = a2; w.aal[k] = (short)aa; w.aal2[k] = (short)aa2; }
 }
 
+// the same reductions by a group of 8 lanes (staging): the partners are spread over the lanes, the per-lane top-2 are merged by
+// three xor-shuffle steps.  `gmask`: the group's lanes; j: lane index within the group.  Result in lane j == 0.
+template <typename R>
+__device__ __forceinline__ void merge_top2(R &o1, int &i1, R &o2, int &i2, R b1, int j1, R b2, int j2) {
+    if (b1 > o1) {
+        if (o1 >= b2) { o2 = o1; i2 = i1; } else { o2 = b2; i2 = j2; }
+        o1 = b1; i1 = j1;
+    } else if (b1 > o2) { o2 = b1; i2 = j1; }
+}
+template <typename R>
+__device__ __forceinline__ void group_top2(const ModelDev &m, WinState<R> &w, int k, int j, uint32_t gmask, R *sx, R *sy) {
+    R o1 = 0, o2 = 0, a1 = 0, a2 = 0;
+    int ao = -1, aa = -1, ao2 = -1, aa2 = -1;
+    const Geo<R> gk = geo_w(w, k);
+    const R rk = w.rad[k];
+    const int n = w.n;
+    for (int v = j; v < n; v += 8) {
+        if (v == k || !(w.flags[v] & W2_ALIVE)) continue;
+        const int dx = w.x[v] - gk.x, dy = w.y[v] - gk.y, d2 = dx * dx + dy * dy;
+        if (d2 > m.max_d2) continue;
+        if (d2 <= m.ov_d2) {
+            const R o = pair_ov_w(m, w, v, gk, rk, d2, sx, sy);
+            if (o > o1) { o2 = o1; ao2 = ao; o1 = o; ao = v; } else if (o > o2) { o2 = o; ao2 = v; }
+        }
+        if (d2 <= m.al_d2) {
+            const R a = align_magnitude(gk, geo_w(w, v), m.rewarding);
+            if (a > a1) { a2 = a1; aa2 = aa; a1 = a; aa = v; } else if (a > a2) { a2 = a; aa2 = v; }
+        }
+    }
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+        const R bo1 = __shfl_xor_sync(gmask, o1, off), bo2 = __shfl_xor_sync(gmask, o2, off);
+        const int bi1 = __shfl_xor_sync(gmask, ao, off), bi2 = __shfl_xor_sync(gmask, ao2, off);
+        const R ba1 = __shfl_xor_sync(gmask, a1, off), ba2 = __shfl_xor_sync(gmask, a2, off);
+        const int bj1 = __shfl_xor_sync(gmask, aa, off), bj2 = __shfl_xor_sync(gmask, aa2, off);
+        merge_top2(o1, ao, o2, ao2, bo1, bi1, bo2, bi2);
+        merge_top2(a1, aa, a2, aa2, ba1, bj1, ba2, bj2);
+    }
+    if (j == 0) {
+        w.ov1[k] = o1; w.ov2[k] = o2; w.aov[k] = (short)ao; w.aov2[k] = (short)ao2;
+        w.al1[k] = a1; w.al2[k] = a2; w.aal[k] = (short)aa; w.aal2[k] = (short)aa2;
+    }
+}
+
 #ifdef MPP_V_FOBJ
 #define MPP_FOBJ_INL __noinline__
 #else
@@ -1401,7 +1445,15 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             w.detv[k] = detv; w.pn0[k] = pn[0]; w.pn1[k] = pn[1]; w.pn2[k] = pn[2];
             w.dm0[k] = (R)dm[0]; w.dm1[k] = (R)dm[1]; w.dm2[k] = (R)dm[2];
         }
-        if (w.flags[k] & W2_INNER) { recompute_top2(m, w, k, true, true, sx, sy); w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]); }
+    }
+    {   // phase E, a group of 8 lanes per object
+        const int gid = sidx >> 3, j = sidx & 7, n_groups = sg >> 3;
+        const uint32_t gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
+        for (int k = gid; k < n0; k += n_groups) {
+            if (!(w.flags[k] & W2_INNER)) continue;
+            group_top2(m, w, k, j, gmask, sx, sy);
+            if (j == 0) w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]);
+        }
     }
     }  // stager
     __syncthreads();
