@@ -56,6 +56,18 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
     constexpr size_t SC = ((size_t)NW * W2_SCRATCH * sizeof(R) + 15) & ~(size_t)15;
     SceneDev<R> &sc = *reinterpret_cast<SceneDev<R> *>(smem + WS + SC);  // this visit's scene (shared-memory copy)
     __shared__ int s_task;
+    // the plan's small arrays in shared memory (decoding a task is a binary search: dependent loads, once per visit)
+    constexpr int PLAN_S = 32;
+    __shared__ int s_plan[4 * PLAN_S + 2 + 9 * PLAN_S + 1];
+    __shared__ float s_temp[PLAN_S];
+    if (plan.n_sweeps <= PLAN_S) {
+        const int S = plan.n_sweeps;
+        int *sox = s_plan, *soy = s_plan + PLAN_S + 1, *slo = s_plan + 2 * PLAN_S + 2, *shi = s_plan + 3 * PLAN_S + 2, *sbase = s_plan + 4 * PLAN_S + 2;
+        for (int k = threadIdx.x; k <= S; k += 32 * NW) { sox[k] = plan.ox[k]; soy[k] = plan.oy[k]; }
+        for (int k = threadIdx.x; k < S; k += 32 * NW) { slo[k] = plan.wi_lo[k]; shi[k] = plan.wi_hi[k]; s_temp[k] = plan.temp[k]; }
+        for (int k = threadIdx.x; k <= 9 * S; k += 32 * NW) sbase[k] = plan.task_base[k];
+        plan.ox = sox; plan.oy = soy; plan.wi_lo = slo; plan.wi_hi = shi; plan.task_base = sbase; plan.temp = s_temp;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {
         if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);

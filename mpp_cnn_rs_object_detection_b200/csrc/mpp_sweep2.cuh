@@ -1339,6 +1339,35 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     } else {
     // phase A (warp 0): window constants; handles / position keys of the objects within 64 px of the window
     if (warp == 0) {
+        // every independent global load of the phase is issued first (one round trip instead of four dependent ones): the masks
+        // of the window's own storage cells (lanes 0-3), the row masses of the window, 1 / total mass, and the masks of the
+        // (at most 36) storage cells within 64 px
+        const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
+        const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
+        int own_cell = -1;
+        uint32_t own_mask = 0xffffffffu;
+        if (lane < 4) {
+            const int cx = (x0 >> 5) + (lane >> 1), cy = (y0 >> 5) + (lane & 1);
+            if (cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5)) {
+                own_cell = cy + cx * c.ny;
+                own_mask = ld_state<SPLIT>(mask_ptr<SPLIT>(c, own_cell));
+            }
+        }
+        double rm = 0.0;
+        {
+            const size_t pitch = (size_t)c.W + 1;
+            if (lane < x1 - x0) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
+        }
+        const double inv_total = c.cell_cdf[c.ncell];  // [ncell] = 1 / total mass
+        int cell0 = 0, cell1 = 0;
+        uint32_t msk0 = 0, msk1 = 0;
+        if (lane < ncells) { cell0 = (sy0 + lane % ncw) + (sx0 + lane / ncw) * c.ny; msk0 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell0)); }
+        if (lane + 32 < ncells) { cell1 = (sy0 + (lane + 32) % ncw) + (sx0 + (lane + 32) / ncw) * c.ny; msk1 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell1)); }
+        // per-visit constants, spread over the lanes
+        if (lane < 8) w.pkf[lane] = c.k.pf[lane];
+        for (int k = lane; k < MPP_WINDOW_STATS; k += 32) w.kstat[k] = 0;
+        if (lane < 4) { w.ccell[lane] = own_cell; w.cmask[lane] = own_mask; }
+        w.row_mass[lane] = (float)rm;
         if (lane == 0) {
             w.x0 = x0; w.x1 = x1; w.y0 = y0; w.y1 = y1;
             w.cx0 = x0 >> 5; w.cy0 = y0 >> 5;
@@ -1347,35 +1376,17 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             // depend on the schedule, on the proposals per visit of other calls, or on how a scene is split across GPUs.  The
             // host refuses sweep numbers whose uids would leave the 31-bit range (uid_space_ok in mpp_b200.cu).
             w.uid_base = 0x80000000u | (uint32_t)(((sweep_id * (uint64_t)((c.nx + 2) * (c.ny + 2)) + (uint64_t)(wi * (c.ny + 2) + wj)) * (uint64_t)W2_PRE) & 0x7fffffffull);
-            for (int q = 0; q < 4; ++q) {
-                const int cx = (x0 >> 5) + (q >> 1), cy = (y0 >> 5) + (q & 1);
-                const bool ok = cx < c.nx && cy < c.ny && cx <= ((x1 - 1) >> 5) && cy <= ((y1 - 1) >> 5);
-                w.ccell[q] = ok ? cy + cx * c.ny : -1;
-                w.cmask[q] = ok ? ld_state<SPLIT>(mask_ptr<SPLIT>(c, cy + cx * c.ny)) : 0xffffffffu;
-            }
-            for (int k = 0; k < 8; ++k) w.pkf[k] = c.k.pf[k];
-            for (int k = 0; k < MPP_WINDOW_STATS; ++k) w.kstat[k] = 0;
             w.pk_e0 = c.k.pk_e0; w.pk_e2 = c.k.pk_e2;
             w.dens_scale = (float)c.H * (float)c.W * 32768.0f / c.det_sum;
             w.lam_unif = (float)(c.k.unif_scale * (double)((x1 - x0) * (y1 - y0)));
         }
-        {   // detection mass of the window rows
-            const size_t pitch = (size_t)c.W + 1;
-            double rm = 0.0;
-            if (lane < x1 - x0) rm = c.rowcum[(size_t)(x0 + lane) * pitch + y1] - c.rowcum[(size_t)(x0 + lane) * pitch + y0];
-            w.row_mass[lane] = (float)rm;
+        {   // detection mass of the window
             const double tot = warp_sum(rm);
-            if (lane == 0) { w.win_mass = tot; w.lam_data = (float)(c.k.intensity * tot * c.cell_cdf[c.ncell]); }  // [ncell] = 1 / total mass
+            if (lane == 0) { w.win_mass = tot; w.lam_data = (float)(c.k.intensity * tot * inv_total); }
         }
-        const int sx0 = max(x0 - 64, 0) >> 5, sx1 = min(x1 + 63, c.H - 1) >> 5, sy0 = max(y0 - 64, 0) >> 5, sy1 = min(y1 + 63, c.W - 1) >> 5;
-        const int ncw = sy1 - sy0 + 1, ncells = (sx1 - sx0 + 1) * ncw;
         int n = 0;
-        // the occupancy masks of the (at most 36) storage cells in one round trip, then the 16-byte record heads two per lane
-        // and round trip (the order in which entries are collected does not matter: phase B sorts them)
-        int cell0 = 0, cell1 = 0;
-        uint32_t msk0 = 0, msk1 = 0;
-        if (lane < ncells) { cell0 = (sy0 + lane % ncw) + (sx0 + lane / ncw) * c.ny; msk0 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell0)); }
-        if (lane + 32 < ncells) { cell1 = (sy0 + (lane + 32) % ncw) + (sx0 + (lane + 32) / ncw) * c.ny; msk1 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell1)); }
+        // the 16-byte record heads, two per lane and round trip (the order in which entries are collected does not matter: phase B
+        // sorts them)
         while (__any_sync(MPP_FULL, (msk0 | msk1) != 0)) {
             uint32_t h[2] = {0, 0};
             int4 head[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
@@ -1399,26 +1410,27 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
         if (n > W2_K) { n = W2_K; if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
         if (lane == 0) { w.n = n; w.n_win = 0; }
+        __syncwarp();
+        MPP_MARK(1);
+        // phase B (still warp 0: no barrier in between): canonical order (by pixel, then uid) so that the chain does not depend
+        // on storage slot order
+        for (int k = lane; k < n; k += 32) {
+            const int key = w.x[k];
+            const uint32_t u = w.uid[k];
+            int rank = 0;
+            for (int v = 0; v < n; ++v) {
+                const int kv = w.x[v];
+                rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
+            }
+            w.order[rank] = w.handle[k];
+        }
     }
     if (!SIMT && NW == 1)  // a single warp does everything, one after the other
         for (int job = 0; job < n_jobs; ++job)
             predraw_births(c, w, job & 1, job >> 1, per_visit, x0, x1, y0, y1, seed, win_id, sweep_id, scratch, lane);
     stage_sync(sg);
-    MPP_MARK(1);
-    const int n0 = w.n;
-    // phase B: canonical order (by pixel, then uid) so that the chain does not depend on storage slot order
-    for (int k = sidx; k < n0; k += sg) {
-        const int key = w.x[k];
-        const uint32_t u = w.uid[k];
-        int rank = 0;
-        for (int v = 0; v < n0; ++v) {
-            const int kv = w.x[v];
-            rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
-        }
-        w.order[rank] = w.handle[k];
-    }
-    stage_sync(sg);
     MPP_MARK(2);
+    const int n0 = w.n;
     // phase C: one thread per object loads its full record
     for (int p = sidx; p < n0; p += sg) {
         const uint32_t h = w.order[p];
@@ -1455,6 +1467,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             if (j == 0) w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]);
         }
     }
+    MPP_MARK(5);
     }  // stager
     __syncthreads();
     MPP_MARK(4);
@@ -1594,10 +1607,11 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     if (dbg_maxdiff && threadIdx.x == 0) {
         const int slot = atomicAdd(reinterpret_cast<int *>(dbg_maxdiff + 1), 1);
         if (slot < 4000) {
-            float *o = dbg_maxdiff + 8 + slot * 12;
+            float *o = dbg_maxdiff + 8 + slot * 14;
             o[0] = (float)w.n; o[1] = (float)w.n_win; o[2] = (float)(t_mark[1] - t_mark[0]); o[3] = (float)(t_mark[2] - t_mark[1]);
             o[4] = (float)(t_mark[3] - t_mark[2]); o[5] = (float)(t_mark[4] - t_mark[3]); o[6] = (float)t_eval; o[7] = (float)t_commit;
             o[8] = (float)n_rounds; o[9] = (float)w.n_acc; o[10] = (float)(clock64() - t_mark[0]); o[11] = (float)w.n_eval;
+            o[12] = (float)(t_mark[5] - t_mark[3]); o[13] = (float)(t_mark[4] - t_mark[5]);
         }
     }
 #endif
@@ -1678,6 +1692,16 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
         for (int k = threadIdx.x; k < (int)(sizeof(Ctx<R>) / 4); k += 32 * NW) dst[k] = src[k];
     }
     __shared__ int s_task;
+    // the plan's small arrays in shared memory: decoding a task is a binary search, i.e. dependent loads, once per visit
+    constexpr int PLAN_S = 48;
+    __shared__ int s_plan[3 * PLAN_S + 1];
+    __shared__ float s_temp[PLAN_S];
+    if (plan.n_sweeps <= PLAN_S) {
+        const int S = plan.n_sweeps;
+        for (int k = threadIdx.x; k < S; k += 32 * NW) { s_plan[k] = plan.ox[k]; s_plan[PLAN_S + k] = plan.oy[k]; s_temp[k] = plan.temp[k]; }
+        for (int k = threadIdx.x; k <= S; k += 32 * NW) s_plan[2 * PLAN_S + k] = plan.task_base[k];
+        plan.ox = s_plan; plan.oy = s_plan + PLAN_S; plan.task_base = s_plan + 2 * PLAN_S; plan.temp = s_temp;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {
         if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);

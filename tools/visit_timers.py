@@ -23,12 +23,12 @@ for nw, pv in ((8, 96),):
     eng.set_maps(det, marks); eng.set_model(spec); eng.set_kernels(intensity=max(1, len(objs)))
     eng.add_objects(objs[:, :2], objs[:, 2:5])
     eng.run_windows(3, pv, nw, t0=0.02, seed=1)
-    dbg = torch.zeros(8 + 4000 * 12, dtype=torch.float32, device=dev)
+    dbg = torch.zeros(8 + 4000 * 14, dtype=torch.float32, device=dev)
     cnt = (C.c_ulonglong * 8)()
     _lib.check(eng.lib.mpp_run_windows(eng.ctx, 1, pv, nw, 1, 0.02, 1.0, 0.0, 1, 3, cnt, dbg.data_ptr()))
     d = dbg.cpu().numpy()
     n = min(4000, int(d[1:2].view(np.int32)[0]))
-    tr = d[8:8 + n * 12].reshape(n, 12)
+    tr = d[8:8 + n * 14].reshape(n, 14)
     print(f"nw={nw} pv={pv}: visits traced {n}")
     occ = tr[:, 1] > 0
     for label, sel in (("empty windows", ~occ), ("occupied windows", occ), ("windows with >= 3 objects", tr[:, 1] >= 3)):
@@ -38,7 +38,7 @@ for nw, pv in ((8, 96),):
                   f"{(t[:, 2] + t[:, 3] + t[:, 4] + t[:, 5]).mean() / 1900:.1f} | eval {t[:, 6].mean() / 1900:.1f} | commit {t[:, 7].mean() / 1900:.1f} | rounds {t[:, 8].mean():.1f} | "
                   f"accepted {t[:, 9].mean():.1f} | staged n {t[:, 0].mean():.1f} | n_win {t[:, 1].mean():.2f}")
     for name, col in (("staged n", 0), ("n_win", 1), ("A heads us", 2), ("B rank us", 3), ("C recs us", 4), ("D+E us", 5), ("eval us", 6), ("commit us", 7),
-                      ("rounds", 8), ("acc", 9), ("total us", 10), ("evaluated", 11)):
+                      ("rounds", 8), ("acc", 9), ("total us", 10), ("evaluated", 11), ("D+E pure us", 12), ("wait predraw us", 13)):
         v = tr[:, col] / 1900.0 if "us" in name else tr[:, col]
         print(f"  {name:12s} mean {v.mean():8.2f}  p50 {np.median(v):8.2f}  p90 {np.percentile(v, 90):8.2f}  max {v.max():8.2f}")
 
