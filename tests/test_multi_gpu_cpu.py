@@ -132,3 +132,45 @@ def test_split_scene_protocol_matches_single_process(world):
             seen.add((s, wi))
             assert ref_log[(s, wi)] == (uids, cols), (rank, s, wi)
     assert seen == set(ref_log)
+
+
+def test_band_geometry_of_the_peer_split():
+    """Host-side geometry of the peer-access split: bands are whole 32-px cell rows covering the scene, map rows add 64 rows either
+    side, every object is stored by exactly one rank, and undersized bands are refused."""
+    import pytest
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg
+
+    class _Eng:  # the geometry needs no device
+        pass
+
+    for h, world in ((8192, 8), (4096, 3), (2048, 2), (1000, 2)):
+        bands = mg.row_bands(h, world)
+        assert bands[0][0] == 0 and bands[-1][1] == h and all(b[1] == n[0] for b, n in zip(bands, bands[1:]))
+        assert all(b[0] % 32 == 0 for b in bands) and all(b[1] % 32 == 0 for b in bands[:-1])
+        xy = np.stack([np.arange(h), np.zeros(h, dtype=int)], axis=1)
+        owners = np.zeros(h, dtype=int)
+        for r in range(world):
+            sc = mg.PeerSplitScene(_Eng(), h, r, world)
+            owners += sc.select_initial(xy).astype(int)
+            m0, m1 = mg.PeerSplitScene.map_rows(h, r, world)
+            assert m0 == max(0, sc.r0 - 64) and m1 == min(h, sc.r1 + 64)
+        assert np.all(owners == 1)
+    with pytest.raises(ValueError):
+        mg.PeerSplitScene(_Eng(), 1000, 0, 4)   # 250-row bands: a window would reach beyond the neighbour band
+    assert mg.shard_items(10, 4, 1) == [1, 5, 9] and sorted(sum((mg.shard_items(256, 8, r) for r in range(8)), [])) == list(range(256))
+
+
+def test_sweep_planning_counts_the_windows_of_the_shifted_grids():
+    from mpp_cnn_rs_object_detection_b200 import multi_gpu as mg
+    from mpp_cnn_rs_object_detection_b200.api.rjmcmc import plan_sweeps
+    shape, seed = (469, 753), 12345
+    pv, n_sweeps, per_sweep = plan_sweeps(shape, seed, 500000, 96)
+    total = 0
+    for s in range(n_sweeps):
+        ox, oy = mg.grid_offset(seed, s)
+        total += ((shape[0] + ox + 31) // 32) * ((shape[1] + oy + 31) // 32) * pv
+    assert pv == 96 and total >= 500000 and total - ((shape[0] + 62) // 32) * ((shape[1] + 62) // 32) * pv < 500000
+    assert abs(per_sweep * n_sweeps - total) < 1e-6
+    # a budget smaller than one sweep lowers the proposals per visit instead of overshooting by a whole sweep
+    pv_small, n_small, _ = plan_sweeps((64, 64), 1, 40, 96)
+    assert n_small >= 1 and pv_small <= 10
