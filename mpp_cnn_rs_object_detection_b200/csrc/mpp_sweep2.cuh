@@ -56,7 +56,7 @@ struct WinState {
     uint32_t order[W2_K];  // staging scratch: handles in canonical order
     short winlist[W2_K];   // SIMT mode: staged indices of the alive window objects
     // speculation results, one slot per warp
-    int res_accept[W2_MAXW], res_eval[W2_MAXW];
+    int res_accept[2][W2_MAXW], res_eval[W2_MAXW];  // res_accept: double-buffered by round parity (a round without a commit has one barrier)
     // per-visit statistics (mpp_window_stats): [0..15] evaluated by (window empty ? 0 : 8) + kernel, [16..31] accepted likewise,
     // [32] identity proposals accepted, [33] visits, [34] visits that found the window empty
     int kstat[MPP_WINDOW_STATS];
@@ -1508,25 +1508,17 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         __syncwarp();
         const bool head = (lane & (G - 1)) == 0;
         const uint32_t bal = __ballot_sync(MPP_FULL, acc && head), evb = __ballot_sync(MPP_FULL, ev && head);
-        if (lane == 0) { w.res_accept[warp] = bal ? warp * L + (__ffs(bal) - 1) / G : 0x7fffffff; w.res_eval[warp] = (int)evb; }
+        if (lane == 0) { w.res_accept[0][warp] = bal ? warp * L + (__ffs(bal) - 1) / G : 0x7fffffff; w.res_eval[warp] = (int)evb; }
         __syncthreads();
         int first = 0x7fffffff;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) first = min(first, w.res_accept[q]);
+        for (int q = 0; q < NW; ++q) first = min(first, w.res_accept[0][q]);
         const int used = first == 0x7fffffff ? P : first + 1;
         if (head && mine < used && ev) {
             atomicAdd(&w.kstat[kern], 1);
             if (mine == first) atomicAdd(&w.kstat[16 + kern], 1);
         }
-        if (warp == 0 && lane == 0) {
-            w.kstat[34] = 1;
-            int evn = 0;
-            for (int q = 0; q < NW; ++q) {
-                const int cnt = min(max(used - q * L, 0), L) * G;  // lanes of warp q whose proposals were consumed
-                evn += __popc((uint32_t)w.res_eval[q] & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
-            }
-            w.n_eval += evn; w.n_done += used;
-        }
+        if (warp == 0 && lane == 0) w.kstat[34] = 1;
         if (first != 0x7fffffff && warp == first / L) {
             const int src = (first % L) * G;
             Eval<R> g;  // the accepted birth, broadcast from the first lane of its group
@@ -1536,7 +1528,6 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             g.a.hl = bcast(a.hl, src); g.a.hw = bcast(a.hw, src); g.a.ca = bcast(a.ca, src); g.a.sa = bcast(a.sa, src);
             g.a.pos = bcast(a.pos, src); g.a.dm0 = bcast(a.dm0, src); g.a.dm1 = bcast(a.dm1, src); g.a.dm2 = bcast(a.dm2, src);
             g.a.detv = bcast(a.detv, src); g.a.pn0 = bcast(a.pn0, src); g.a.pn1 = bcast(a.pn1, src); g.a.pn2 = bcast(a.pn2, src);
-            if (lane == 0) { w.n_acc += 1; w.n_birth += 1; }
             if (w.n >= W2_K) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
             else {
                 fill_pairs(m, w, -1, true, g.a, lane, sx, sy, po, pa);
@@ -1560,6 +1551,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         t_eval = clock64() - t_s; n_rounds = w.n_acc + 1;
 #endif
     }
+    int buf = 1;  // (buffer 0 of res_accept was used by the empty-window pass)
     while (it < per_visit) {
         Eval<R> e;
         const int mine = it + warp;
@@ -1568,41 +1560,34 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
 #endif
         if (mine < per_visit) evaluate_proposal<R, DBG>(c, w, seed, win_id, sweep_id, mine, temp, lane, sx, sy, po, pa, &e, dbg_maxdiff, tr ? tr + mine : nullptr);
         else { e.accept = false; e.evaluated = false; e.has_add = false; e.r = -1; e.noop = false; e.hyp = 0; e.kernel = 0; }
-        if (lane == 0) { w.res_accept[warp] = e.accept ? (e.noop ? 2 : 1) : 0; w.res_eval[warp] = e.evaluated ? 1 : 0; }
+        if (lane == 0) w.res_accept[buf][warp] = e.accept ? (e.noop ? 2 : 1) : 0;
         __syncthreads();
 #ifdef MPP_TRACE
         const long long t_b = clock64();
 #endif
         int first = NW;
 #pragma unroll
-        for (int q = NW - 1; q >= 0; --q) if (w.res_accept[q] == 1) first = q;  // first accepted proposal that changes the state
+        for (int q = NW - 1; q >= 0; --q) if (w.res_accept[buf][q] == 1) first = q;  // first accepted proposal that changes the state
         const int used = min(first + 1, min(NW, per_visit - it));  // proposals of the chain consumed by this round
-        if (lane == 0 && warp < used && e.evaluated) {
+        if (lane == 0 && warp < used && e.evaluated) {  // the visit's counters are the sums of these tallies
             atomicAdd(&w.kstat[8 * e.hyp + e.kernel], 1);
             if (e.accept && (e.noop || warp == first)) atomicAdd(&w.kstat[16 + 8 * e.hyp + e.kernel], 1);
             if (e.accept && e.noop) atomicAdd(&w.kstat[32], 1);
         }
-        if (warp == 0 && lane == 0) {
-            int ev = 0, same = 0;
-            for (int q = 0; q < used; ++q) { ev += w.res_eval[q]; same += w.res_accept[q] == 2; }
-            w.n_eval += ev; w.n_done += used;
-            if (same) atomicAdd(&w.n_acc, same);  // the committing warp updates the same counter
-        }
-        if (first < NW && warp == first) {
-            if (lane == 0) {
-                atomicAdd(&w.n_acc, 1);
-                if (e.has_add && e.r < 0) w.n_birth += 1;
-                if (!e.has_add && e.r >= 0) w.n_death += 1;
+        if (first < NW) {  // a state-changing proposal was accepted: its warp commits it, the others wait for the new state
+            if (warp == first) {
+                if (w.n >= W2_K && e.has_add && e.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
+                else commit_proposal<R, SPLIT>(c, w, e, mine, lane, sx, sy, po, pa);
             }
-            if (w.n >= W2_K && e.has_add && e.r < 0) { if (lane == 0) atomicOr(c.err, ERRF_NEIGHBOURHOOD); }
-            else commit_proposal<R, SPLIT>(c, w, e, mine, lane, sx, sy, po, pa);
+            __syncthreads();
         }
-        __syncthreads();
 #ifdef MPP_TRACE
         t_eval += t_b - t_a; t_commit += clock64() - t_b; ++n_rounds;
 #endif
         it += used;
+        buf ^= 1;
     }
+    __syncthreads();  // the tallies of the last round are complete before they are published
 #ifdef MPP_TRACE
     if (dbg_maxdiff && threadIdx.x == 0) {
         const int slot = atomicAdd(reinterpret_cast<int *>(dbg_maxdiff + 1), 1);
@@ -1610,7 +1595,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             float *o = dbg_maxdiff + 8 + slot * 14;
             o[0] = (float)w.n; o[1] = (float)w.n_win; o[2] = (float)(t_mark[1] - t_mark[0]); o[3] = (float)(t_mark[2] - t_mark[1]);
             o[4] = (float)(t_mark[3] - t_mark[2]); o[5] = (float)(t_mark[4] - t_mark[3]); o[6] = (float)t_eval; o[7] = (float)t_commit;
-            o[8] = (float)n_rounds; o[9] = (float)w.n_acc; o[10] = (float)(clock64() - t_mark[0]); o[11] = (float)w.n_eval;
+            o[8] = (float)n_rounds; { int na = 0, ne = 0; for (int k = 0; k < 16; ++k) { ne += w.kstat[k]; na += w.kstat[16 + k]; } o[9] = (float)na; o[11] = (float)ne; } o[10] = (float)(clock64() - t_mark[0]);
             o[12] = (float)(t_mark[5] - t_mark[3]); o[13] = (float)(t_mark[4] - t_mark[5]);
         }
     }
@@ -1626,11 +1611,18 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             if (SPLIT) __threadfence_system(); else __threadfence();
             for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
         }
-        atomicAdd(c.counters + 0, (unsigned long long)w.n_done);
-        atomicAdd(c.counters + 1, (unsigned long long)w.n_acc);
-        atomicAdd(c.counters + 2, (unsigned long long)w.n_birth);
-        atomicAdd(c.counters + 3, (unsigned long long)w.n_death);
-        atomicAdd(c.counters + 4, (unsigned long long)w.n_eval);
+        int n_done = w.n_done, n_acc = w.n_acc, n_birth = w.n_birth, n_death = w.n_death, n_eval = w.n_eval;
+        if (!SIMT) {  // warp-per-proposal mode: the counters are sums of the per-kernel tallies
+            n_done = per_visit; n_eval = 0; n_acc = 0;
+            for (int k = 0; k < 16; ++k) { n_eval += w.kstat[k]; n_acc += w.kstat[16 + k]; }
+            n_birth = w.kstat[16] + w.kstat[18] + w.kstat[24] + w.kstat[26];
+            n_death = w.kstat[17] + w.kstat[19] + w.kstat[25] + w.kstat[27];
+        }
+        atomicAdd(c.counters + 0, (unsigned long long)n_done);
+        atomicAdd(c.counters + 1, (unsigned long long)n_acc);
+        atomicAdd(c.counters + 2, (unsigned long long)n_birth);
+        atomicAdd(c.counters + 3, (unsigned long long)n_death);
+        atomicAdd(c.counters + 4, (unsigned long long)n_eval);
         if (w.dn) atomicAdd(c.n_objects, w.dn);
     }
 }
