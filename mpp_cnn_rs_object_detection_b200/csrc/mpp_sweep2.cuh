@@ -114,10 +114,21 @@ __device__ __forceinline__ void gather_pixel(const Ctx<R> &c, int x, int y, uint
 }
 
 // out-of-line copy for the warp-uniform callers of the rounds (every lane issues the same seven gathers: one transaction each)
+// (the seven values come back by value, in registers: through pointers they forced the caller's candidate onto the local stack)
+struct PixelInfo { float detv, pn0, pn1, pn2, dm0, dm1, dm2; };
 template <typename R>
-__device__ __noinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
+__device__ __noinline__ PixelInfo pixel_info_v(const Ctx<R> &c, int x, int y, uint32_t cls) {
+    PixelInfo o;
+    float pn[3], dm[3];
+    gather_pixel(c, x, y, cls, &o.detv, pn, dm);
+    o.pn0 = pn[0]; o.pn1 = pn[1]; o.pn2 = pn[2]; o.dm0 = dm[0]; o.dm1 = dm[1]; o.dm2 = dm[2];
+    return o;
+}
+template <typename R>
+__device__ __forceinline__ void pixel_info(const Ctx<R> &c, int x, int y, uint32_t cls, int lane, float *detv, float *pn, float *dm) {
     (void)lane;
-    gather_pixel(c, x, y, cls, detv, pn, dm);
+    const PixelInfo o = pixel_info_v<R>(c, x, y, cls);
+    *detv = o.detv; pn[0] = o.pn0; pn[1] = o.pn1; pn[2] = o.pn2; dm[0] = o.dm0; dm[1] = o.dm1; dm[2] = o.dm2;
 }
 
 template <typename R>
@@ -225,12 +236,18 @@ __device__ __forceinline__ void group_top2(const ModelDev &m, WinState<R> &w, in
 #endif
 // unit part of the combinator's gated linear form (combine_fast) for staged entry k: everything but the two partner terms
 template <typename R>
+__device__ __forceinline__ void unit_form_vals(const ModelDev &m, R tm0, R tm1, R tm2, R hl, R hw, R ratio, R pos, R *fa, R *fg) {
+    const R uin = (R)m.c_m0 * tm0 + (R)m.c_m1 * tm1 + (R)m.c_m2 * tm2 + (R)m.c_area * area_prior_fast<R>(m, hl, hw) +
+                  (R)m.c_ratio * r_abs((R)m.f_target_ratio - ratio);
+    const R g = (m.gate && !(pos <= (R)m.gate_thr)) ? (R)0 : (R)1;
+    *fa = (R)m.c_pos * pos + g * uin + (R)m.c_0;
+    *fg = g;
+}
+template <typename R>
 __device__ __forceinline__ void unit_form(const ModelDev &m, WinState<R> &w, int k) {
-    const R uin = (R)m.c_m0 * w.tm0[k] + (R)m.c_m1 * w.tm1[k] + (R)m.c_m2 * w.tm2[k] + (R)m.c_area * area_prior_fast<R>(m, w.hl[k], w.hw[k]) +
-                  (R)m.c_ratio * r_abs((R)m.f_target_ratio - w.ratio[k]);
-    const R g = (m.gate && !(w.pos[k] <= (R)m.gate_thr)) ? (R)0 : (R)1;
-    w.fa[k] = (R)m.c_pos * w.pos[k] + g * uin + (R)m.c_0;
-    w.fg[k] = g;
+    R fa, fg;
+    unit_form_vals<R>(m, w.tm0[k], w.tm1[k], w.tm2[k], w.hl[k], w.hw[k], w.ratio[k], w.pos[k], &fa, &fg);
+    w.fa[k] = fa; w.fg[k] = fg;
 }
 template <typename R>
 __device__ MPP_FOBJ_INL R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
@@ -650,28 +667,34 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
             }
             if (s < 0) s = n;  // n < W2_K is guaranteed by the caller
         }
+        // everything the new entry needs is computed from the candidate's registers (warp-uniform); lane 0 then only stores
+        const Cand<R> &a = e.a;
+        R tm0, tm1, tm2, fa, fg;
+        shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &tm0, &tm1, &tm2);
+        unit_form_vals<R>(m, tm0, tm1, tm2, a.hl, a.hw, a.ratio, a.pos, &fa, &fg);
+        const R rad = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+        const uint32_t uid = w.uid_base + (uint32_t)it;
         if (lane == 0) {
-            const Cand<R> &a = e.a;
             if (s == w.n) w.n = s + 1;
             const int ci = ((a.x >> 5) - w.cx0) * 2 + ((a.y >> 5) - w.cy0);
-            const int slot = __ffs(~w.cmask[ci]) - 1;
+            const uint32_t cm = w.cmask[ci];
+            const int slot = __ffs(~cm) - 1;
             const uint32_t h = (uint32_t)w.ccell[ci] * 32u + slot;
-            w.x[s] = a.x; w.y[s] = a.y; w.cls[s] = a.cls; w.handle[s] = h; w.uid[s] = w.uid_base + (uint32_t)it;
-            w.size[s] = a.size; w.ratio[s] = a.ratio; w.angle[s] = a.angle;
-            w.hl[s] = a.hl; w.hw[s] = a.hw; w.ca[s] = a.ca; w.sa[s] = a.sa; w.rad[s] = r_sqrt(a.hl * a.hl + a.hw * a.hw);
-            w.pos[s] = a.pos; w.dm0[s] = a.dm0; w.dm1[s] = a.dm1; w.dm2[s] = a.dm2;
-            shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &w.tm0[s], &w.tm1[s], &w.tm2[s]);
-            w.detv[s] = a.detv; w.pn0[s] = a.pn0; w.pn1[s] = a.pn1; w.pn2[s] = a.pn2;
-            w.flags[s] = W2_ALIVE | W2_WIN | W2_INNER;
-            unit_form(m, w, s);
-            w.n_win += 1; w.dn += 1; w.masks_dirty = 1;
             Rec<R> rec;
-            rec.x = a.x; rec.y = a.y; rec.cls = a.cls; rec.uid = w.uid[s];
+            rec.x = a.x; rec.y = a.y; rec.cls = a.cls; rec.uid = uid;
             rec.size = a.size; rec.ratio = a.ratio; rec.angle = a.angle;
-            rec.e_pos = a.pos; rec.e_m[0] = w.tm0[s]; rec.e_m[1] = w.tm1[s]; rec.e_m[2] = w.tm2[s];
+            rec.e_pos = a.pos; rec.e_m[0] = tm0; rec.e_m[1] = tm1; rec.e_m[2] = tm2;
             rec.hl = a.hl; rec.hw = a.hw; rec.ca = a.ca; rec.sa = a.sa; rec.pad = 0;
             store_rec(rec_ptr<SPLIT>(c, h), rec);
-            w.cmask[ci] |= 1u << slot;
+            w.cmask[ci] = cm | (1u << slot);
+            w.x[s] = a.x; w.y[s] = a.y; w.cls[s] = a.cls; w.handle[s] = h; w.uid[s] = uid;
+            w.size[s] = a.size; w.ratio[s] = a.ratio; w.angle[s] = a.angle;
+            w.hl[s] = a.hl; w.hw[s] = a.hw; w.ca[s] = a.ca; w.sa[s] = a.sa; w.rad[s] = rad;
+            w.pos[s] = a.pos; w.dm0[s] = a.dm0; w.dm1[s] = a.dm1; w.dm2[s] = a.dm2;
+            w.tm0[s] = tm0; w.tm1[s] = tm1; w.tm2[s] = tm2; w.fa[s] = fa; w.fg[s] = fg;
+            w.detv[s] = a.detv; w.pn0[s] = a.pn0; w.pn1[s] = a.pn1; w.pn2[s] = a.pn2;
+            w.flags[s] = W2_ALIVE | W2_WIN | W2_INNER;
+            w.n_win += 1; w.dn += 1; w.masks_dirty = 1;
         }
     }
     __syncwarp();
