@@ -18,6 +18,13 @@
 #define W2_MAXW 8        // warps per window (speculation depth)
 #define W2_PRE 128       // proposals per visit that can be drawn ahead (= the largest proposals_per_visit)
 #define W2_EPS 1e-16f
+// quotients of the Green ratio (proposal densities, Delta E / T): the approximate division (2 ulp) is far inside the float32
+// noise of log alpha and saves the refinement steps + range check of the IEEE one on the critical path of every proposal
+#ifndef MPP_EXACT_DIV
+#define W2_DIV(a, b) __fdividef((a), (b))
+#else
+#define W2_DIV(a, b) ((a) / (b))
+#endif
 #define W2_SCRATCH (32 + 2 * W2_K)  // per-warp scratch (elements): window row masses of the pre-draw + pair-value stash
 
 enum : unsigned char { W2_ALIVE = 1, W2_WIN = 2, W2_INNER = 4 };
@@ -83,7 +90,11 @@ struct Cand {  // the object a proposal wants to add (warp-uniform registers)
 template <typename R>
 __device__ __forceinline__ void shape_terms(const ModelDev &m, R dm0, R dm1, R dm2, R *t0, R *t1, R *t2) {
     if (m.setup == MPP_SETUP_LEGACY) {  // float(np.mean([d0,d1,d2])) data_energies.py:43
-        *t0 = (R)__fdiv_rn(__fadd_rn(__fadd_rn((float)dm0, (float)dm1), (float)dm2), 3.0f);
+        // sum / 3, correctly rounded like the IEEE quotient (reciprocal product + one FMA correction step: exact for the
+        // divisor 3) without the range check and slow path of the division
+        const float sum3 = __fadd_rn(__fadd_rn((float)dm0, (float)dm1), (float)dm2);
+        const float q3 = __fmul_rn(sum3, 0.333333343267440796f);
+        *t0 = (R)__fmaf_rn(__fmaf_rn(-3.0f, q3, sum3), 0.333333343267440796f, q3);
         *t1 = 0; *t2 = 0;
     } else {
         *t0 = dm0; *t1 = dm1; *t2 = dm2;
@@ -150,7 +161,7 @@ __device__ __forceinline__ R pair_ov_w(const ModelDev &m, const WinState<R> &w, 
     if (m.setup == MPP_SETUP_TOY) return d2 <= m.toy_d2 ? (R)m.toy_pair : (R)0;
     const R rr = w.rad[k] + rad_b;
     if ((R)d2 > rr * rr * (R)1.0001) return (R)0;
-    return overlap_energy(geo_w(w, k), gb, sx, sy);
+    return overlap_energy_v<R, true>(w.x[k], w.y[k], w.hl[k], w.hw[k], w.ca[k], w.sa[k], gb.x, gb.y, gb.hl, gb.hw, gb.ca, gb.sa);
 }
 
 // top-2 partner reductions of staged entry k over every other alive staged entry (one lane, serial loop)
@@ -252,7 +263,7 @@ __device__ __forceinline__ void unit_form(const ModelDev &m, WinState<R> &w, int
 template <typename R>
 __device__ MPP_FOBJ_INL R f_obj(const ModelDev &m, const WinState<R> &w, int k, R ov, R al) {
     const R e = w.fa[k] + w.fg[k] * ((R)m.c_ov * ov + (R)m.c_al * ((m.rewarding ? (R)-1 : (R)1) * al));
-    return m.logistic ? (R)2 / ((R)1 + r_exp(-e)) - (R)1 : e;
+    return m.logistic ? r_logistic_pm1(e) : e;
 }
 
 // Delta-energy of removing staged entry r (r < 0: none) and/or adding `a` (has_add), from the staged state only.
@@ -261,7 +272,7 @@ __device__ MPP_FOBJ_INL R f_obj(const ModelDev &m, const WinState<R> &w, int k, 
 template <typename R>
 __device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, int lane, R *sx, R *sy, R *po, R *pa) {
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
-    const R rad_a = has_add ? r_sqrt(a.hl * a.hl + a.hw * a.hw) : (R)0;
+    const R rad_a = has_add ? r_sqrt_fast(a.hl * a.hl + a.hw * a.hw) : (R)0;
     const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
     R acc = 0, ov_add = 0, al_add = 0;
     const int n = w.n;
@@ -290,9 +301,9 @@ __device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w,
         }
         if (has_add) { po[k] = o; pa[k] = al; }
     }
-    acc = warp_sum(acc);
+    acc = warp_sum_sparse(acc);
     if (has_add) {
-        ov_add = warp_max(ov_add); al_add = warp_max(al_add);
+        ov_add = warp_max_nonneg(ov_add); al_add = warp_max_nonneg(al_add);
         Terms<R> t;
         t.pos = a.pos;
         shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &t.m0, &t.m1, &t.m2);
@@ -463,30 +474,30 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
     const float temp_it = visit_temp(c, temp, it);
     switch (kernel) {
     case 0: {  // uniform birth in the window (candidate drawn ahead)
-        const float fwd = pk_of(w, 0, nc) / w.lam_unif;
-        const float bwd = pk_of(w, 1, nc + 1) / (float)(nc + 1);
+        const float fwd = W2_DIV(pk_of(w, 0, nc), w.lam_unif);
+        const float bwd = W2_DIV(pk_of(w, 1, nc + 1), (float)(nc + 1));
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
     }
     case 1: {  // uniform death
-        const float fwd = pk_of(w, 1, nc) / (float)nc;
-        const float bwd = pk_of(w, 0, nc - 1) / w.lam_unif;
+        const float fwd = W2_DIV(pk_of(w, 1, nc), (float)nc);
+        const float bwd = W2_DIV(pk_of(w, 0, nc - 1), w.lam_unif);
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         break;
     }
     case 2: {  // data-driven birth in the window (candidate drawn ahead)
         if (!(w.win_mass > 0.0)) { valid = false; break; }
-        const float fwd = pk_of(w, 2, nc) * dens_of(w, w.pc_detv[hyp][it], w.pc_pn0[hyp][it], w.pc_pn1[hyp][it], w.pc_pn2[hyp][it]) / w.lam_data;
-        const float bwd = pk_of(w, 3, nc + 1) / (float)(nc + 1);
+        const float fwd = W2_DIV(pk_of(w, 2, nc) * dens_of(w, w.pc_detv[hyp][it], w.pc_pn0[hyp][it], w.pc_pn1[hyp][it], w.pc_pn2[hyp][it]), w.lam_data);
+        const float bwd = W2_DIV(pk_of(w, 3, nc + 1), (float)(nc + 1));
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
     }
     case 3: {  // data-driven death
         if (!(w.win_mass > 0.0)) { valid = false; break; }
-        const float fwd = pk_of(w, 3, nc) / (float)nc;
-        const float bwd = pk_of(w, 2, nc - 1) * dens_of(w, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]) / w.lam_data;
+        const float fwd = W2_DIV(pk_of(w, 3, nc), (float)nc);
+        const float bwd = W2_DIV(pk_of(w, 2, nc - 1) * dens_of(w, w.detv[r], w.pn0[r], w.pn1[r], w.pn2[r]), w.lam_data);
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         break;
     }
@@ -525,7 +536,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (lane < BX1 - BX0) rb = (float)(c.rowcum[(size_t)(BX0 + lane) * pitch + BY1] - c.rowcum[(size_t)(BX0 + lane) * pitch + BY0]);
         pixel_info(c, a.x, a.y, a.cls, lane, &a.detv, pn, dm);
         const float tot_e = warp_sum(rb);
-        const float fwd = a.detv / tot_s, bwd = w.detv[r] / tot_e;  // p_kernel / n cancel
+        const float fwd = W2_DIV(a.detv, tot_s), bwd = W2_DIV(w.detv[r], tot_e);  // p_kernel / n cancel
         log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
         e->has_add = true;
         break;
@@ -552,7 +563,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             nv = mark_edge<R>(pid, ncls);
             // the object's own class was drawn and its mark already sits on that class's value: same object
             if (ncls == ocls && nv == (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r]))) { e->noop = true; break; }
-            const float pf = __shfl_sync(MPP_FULL, v, ncls) / s, pb = __shfl_sync(MPP_FULL, v, ocls) / s;
+            const float pf = W2_DIV(__shfl_sync(MPP_FULL, v, ncls), s), pb = W2_DIV(__shfl_sync(MPP_FULL, v, ocls), s);
             log_ratio = __logf(pb + W2_EPS) - __logf(pf + W2_EPS);  // p_kernel / n cancel
         }
         const float pnew = __shfl_sync(MPP_FULL, v, ncls);
@@ -562,7 +573,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         a.detv = w.detv[r];
         pn[0] = w.pn0[r]; pn[1] = w.pn1[r]; pn[2] = w.pn2[r];
         dm[0] = (float)w.dm0[r]; dm[1] = (float)w.dm1[r]; dm[2] = (float)w.dm2[r];
-        pn[pid] = pnew / s;
+        pn[pid] = __fdividef(pnew, s);  // (as gather_pixel normalises the staged probabilities)
         dm[pid] = mark_energy_f32(m, pid, pnew);
         e->has_add = true;
         break;
@@ -593,8 +604,12 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             a.pos = (R)position_energy_f32(a.detv, m.pos_thr);
             a.dm0 = (R)dm[0]; a.dm1 = (R)dm[1]; a.dm2 = (R)dm[2];
             a.pn0 = pn[0]; a.pn1 = pn[1]; a.pn2 = pn[2];
-            const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
-            a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+            if (a.size == w.size[r] && a.ratio == w.ratio[r]) {  // a translation or an angle transform keeps the half extents
+                a.hl = w.hl[r]; a.hw = w.hw[r];
+            } else {
+                const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
+                a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
+            }
             if (a.angle == w.angle[r]) {
                 a.ca = w.ca[r]; a.sa = w.sa[r];
             } else {
@@ -631,7 +646,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (lane == 0) atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
     }
 #endif
-    const float la = -(float)de / temp_it + log_ratio;
+    const float la = W2_DIV(-(float)de, temp_it) + log_ratio;
     e->evaluated = true;
     e->accept = __logf(u01f(q1.w) + W2_EPS) < la;
     if (DBG && tr && lane == 0)
@@ -672,7 +687,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         R tm0, tm1, tm2, fa, fg;
         shape_terms<R>(m, a.dm0, a.dm1, a.dm2, &tm0, &tm1, &tm2);
         unit_form_vals<R>(m, tm0, tm1, tm2, a.hl, a.hw, a.ratio, a.pos, &fa, &fg);
-        const R rad = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+        const R rad = r_sqrt_fast(a.hl * a.hl + a.hw * a.hw);
         const uint32_t uid = w.uid_base + (uint32_t)it;
         if (lane == 0) {
             if (s == w.n) w.n = s + 1;
@@ -761,17 +776,17 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         return;
     }
     if (s >= 0) {  // merge the per-lane top-2 of (po, pa) into the new object's reductions (ties: lowest lane first)
-        const R mo = warp_max(n_o1);
+        const R mo = warp_max_nonneg(n_o1);
         const int lo = __ffs(__ballot_sync(MPP_FULL, n_o1 == mo)) - 1;
         const R co = lane == lo ? n_o2 : n_o1;
-        const R so = warp_max(co);
+        const R so = warp_max_nonneg(co);
         const int lo2 = __ffs(__ballot_sync(MPP_FULL, co == so)) - 1;
         const int ao = __shfl_sync(MPP_FULL, n_ao, lo);
         const int ao2 = __shfl_sync(MPP_FULL, lane == lo ? n_ao2 : n_ao, lo2);
-        const R ma = warp_max(n_a1);
+        const R ma = warp_max_nonneg(n_a1);
         const int la = __ffs(__ballot_sync(MPP_FULL, n_a1 == ma)) - 1;
         const R ca2 = lane == la ? n_a2 : n_a1;
-        const R sa2 = warp_max(ca2);
+        const R sa2 = warp_max_nonneg(ca2);
         const int la2 = __ffs(__ballot_sync(MPP_FULL, ca2 == sa2)) - 1;
         const int aa = __shfl_sync(MPP_FULL, n_aa, la);
         const int aa2 = __shfl_sync(MPP_FULL, lane == la ? n_aa2 : n_aa, la2);
@@ -904,7 +919,7 @@ __device__ __noinline__ void predraw_births(const Ctx<R> &c, WinState<R> &w, int
 template <typename R>
 __device__ __forceinline__ R delta_lane(const ModelDev &m, const WinState<R> &w, int r, bool has_add, const Cand<R> &a, R *sx, R *sy) {
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
-    const R rad_a = has_add ? r_sqrt(a.hl * a.hl + a.hw * a.hw) : (R)0;
+    const R rad_a = has_add ? r_sqrt_fast(a.hl * a.hl + a.hw * a.hw) : (R)0;
     const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
     R acc = 0, ov_add = 0, al_add = 0;
     const int n = w.n;
@@ -1169,7 +1184,7 @@ __device__ __forceinline__ void fill_pairs(const ModelDev &m, const WinState<R> 
                                            R *po, R *pa) {
     if (!has_add) return;
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
-    const R rad_a = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+    const R rad_a = r_sqrt_fast(a.hl * a.hl + a.hw * a.hw);
     const int n = w.n;
     for (int k = lane; k < n; k += 32) {
         R o = 0, al = 0;
@@ -1232,7 +1247,7 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
     R acc = 0, ov_add = 0, al_add = 0;
     if (live) {
         Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
-        const R rad_a = r_sqrt(a.hl * a.hl + a.hw * a.hw);
+        const R rad_a = r_sqrt_fast(a.hl * a.hl + a.hw * a.hw);
         for (int i = j; i < n_near; i += G) {  // `near`: the alive staged objects within reach of the window (W2_INNER), ascending
             const int k = near[i];
             const int dx = w.x[k] - a.x, dy = w.y[k] - a.y, d2 = dx * dx + dy * dy;
@@ -1268,10 +1283,10 @@ __device__ __noinline__ bool evaluate_birth_group(const Ctx<R> &c, const WinStat
         atomicMax(reinterpret_cast<int *>(dbg_maxdiff), __float_as_int(diff));
     }
 #endif
-    const float fwd = kernel == 0 ? pk_of(w, 0, 0) / w.lam_unif : pk_of(w, 2, 0) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2) / w.lam_data;
+    const float fwd = kernel == 0 ? W2_DIV(pk_of(w, 0, 0), w.lam_unif) : W2_DIV(pk_of(w, 2, 0) * dens_of(w, a.detv, a.pn0, a.pn1, a.pn2), w.lam_data);
     const float bwd = pk_of(w, kernel + 1, 1);  // / (nc + 1) = 1
     const float log_ratio = __logf(bwd + W2_EPS) - __logf(fwd + W2_EPS);
-    const bool accept = __logf(u01f(w.pq[7][it]) + W2_EPS) < -(float)de / visit_temp(c, temp, it) + log_ratio;
+    const bool accept = __logf(u01f(w.pq[7][it]) + W2_EPS) < W2_DIV(-(float)de, visit_temp(c, temp, it)) + log_ratio;
     if (DBG && tr && j == 0)
         trace_write<R>(tr + it, MPP_TRACE_HAS_ADD | MPP_TRACE_EVALUATED | (accept ? MPP_TRACE_ACCEPT : 0u), kernel, 0, 0, 0u, w.uid_base + (uint32_t)it, a,
                        (float)de, log_ratio, visit_temp(c, temp, it), w.pq[0][it], w.pq[1][it], w.pq[7][it]);
@@ -1400,7 +1415,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             // host refuses sweep numbers whose uids would leave the 31-bit range (uid_space_ok in mpp_b200.cu).
             w.uid_base = 0x80000000u | (uint32_t)(((sweep_id * (uint64_t)((c.nx + 2) * (c.ny + 2)) + (uint64_t)(wi * (c.ny + 2) + wj)) * (uint64_t)W2_PRE) & 0x7fffffffull);
             w.pk_e0 = c.k.pk_e0; w.pk_e2 = c.k.pk_e2;
-            w.dens_scale = (float)c.H * (float)c.W * 32768.0f / c.det_sum;
+            w.dens_scale = W2_DIV((float)c.H * (float)c.W * 32768.0f, c.det_sum);
             w.lam_unif = (float)(c.k.unif_scale * (double)((x1 - x0) * (y1 - y0)));
         }
         {   // detection mass of the window
@@ -1437,13 +1452,14 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         MPP_MARK(1);
         // phase B (still warp 0: no barrier in between): canonical order (by pixel, then uid) so that the chain does not depend
         // on storage slot order
+        // (branch-free: one 64-bit (pixel key, uid) comparison per pair, the entries read by broadcast)
         for (int k = lane; k < n; k += 32) {
-            const int key = w.x[k];
-            const uint32_t u = w.uid[k];
+            const unsigned long long key = ((unsigned long long)(uint32_t)w.x[k] << 32) | (unsigned long long)w.uid[k];
             int rank = 0;
+#pragma unroll 4
             for (int v = 0; v < n; ++v) {
-                const int kv = w.x[v];
-                rank += (kv < key) || (kv == key && (w.uid[v] < u || (w.uid[v] == u && v < k)));
+                const unsigned long long kv = ((unsigned long long)(uint32_t)w.x[v] << 32) | (unsigned long long)w.uid[v];
+                rank += (int)(kv < key) + (int)((kv == key) & (v < k));
             }
             w.order[rank] = w.handle[k];
         }
@@ -1462,7 +1478,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const bool inner = rec.x >= x0 - 32 && rec.x < x1 + 32 && rec.y >= y0 - 32 && rec.y < y1 + 32;
         w.x[p] = rec.x; w.y[p] = rec.y; w.cls[p] = rec.cls; w.handle[p] = h; w.uid[p] = rec.uid;
         w.size[p] = rec.size; w.ratio[p] = rec.ratio; w.angle[p] = rec.angle;
-        w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa; w.rad[p] = r_sqrt(rec.hl * rec.hl + rec.hw * rec.hw);
+        w.hl[p] = rec.hl; w.hw[p] = rec.hw; w.ca[p] = rec.ca; w.sa[p] = rec.sa; w.rad[p] = r_sqrt_fast(rec.hl * rec.hl + rec.hw * rec.hw);
         w.pos[p] = rec.e_pos; w.tm0[p] = rec.e_m[0]; w.tm1[p] = rec.e_m[1]; w.tm2[p] = rec.e_m[2];
         w.flags[p] = W2_ALIVE | (inw ? W2_WIN : 0) | (inner ? W2_INNER : 0);
         unit_form(m, w, p);
@@ -1509,9 +1525,9 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const long long t_p = clock64();
 #endif
         const int L0 = (per_visit + NW - 1) / NW;                          // proposals per warp
-        const int L = L0 <= 1 ? 1 : (L0 <= 2 ? 2 : (L0 <= 4 ? 4 : (L0 <= 8 ? 8 : (L0 <= 16 ? 16 : 32))));
-        const int G = 32 / L, P = min(per_visit, L * NW);
-        const int mine = warp * L + lane / G;
+        const int lgL = L0 <= 1 ? 0 : (L0 <= 2 ? 1 : (L0 <= 4 ? 2 : (L0 <= 8 ? 3 : (L0 <= 16 ? 4 : 5))));  // (powers of two: shifts, no divisions)
+        const int L = 1 << lgL, G = 32 >> lgL, P = min(per_visit, L * NW);
+        const int mine = warp * L + (lane >> (5 - lgL));
         // only the staged objects within 32 px of the window can interact with a birth inside it: compact their indices
         // (per warp, in the pair-value stash, which is free until a commit)
         int *near = reinterpret_cast<int *>(po);
@@ -1531,7 +1547,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         __syncwarp();
         const bool head = (lane & (G - 1)) == 0;
         const uint32_t bal = __ballot_sync(MPP_FULL, acc && head), evb = __ballot_sync(MPP_FULL, ev && head);
-        if (lane == 0) { w.res_accept[0][warp] = bal ? warp * L + (__ffs(bal) - 1) / G : 0x7fffffff; w.res_eval[warp] = (int)evb; }
+        if (lane == 0) { w.res_accept[0][warp] = bal ? warp * L + ((__ffs(bal) - 1) >> (5 - lgL)) : 0x7fffffff; w.res_eval[warp] = (int)evb; }
         __syncthreads();
         int first = 0x7fffffff;
 #pragma unroll
@@ -1542,8 +1558,8 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
             if (mine == first) atomicAdd(&w.kstat[16 + kern], 1);
         }
         if (warp == 0 && lane == 0) w.kstat[34] = 1;
-        if (first != 0x7fffffff && warp == first / L) {
-            const int src = (first % L) * G;
+        if (first != 0x7fffffff && warp == (first >> lgL)) {
+            const int src = (first & (L - 1)) * G;
             Eval<R> g;  // the accepted birth, broadcast from the first lane of its group
             g.kernel = bcast(kern, src); g.r = -1; g.has_add = true; g.evaluated = true; g.accept = true;
             g.a.x = bcast(a.x, src); g.a.y = bcast(a.y, src); g.a.cls = bcast(a.cls, src);
