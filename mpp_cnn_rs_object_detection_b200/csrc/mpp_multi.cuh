@@ -42,6 +42,11 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed_sys(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -117,14 +122,19 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
                     const int ni = wi + lane / 5 - 2, nj = wj + lane % 5 - 2;
                     if (ni >= 0 && nj >= 0 && ni < nwx && nj < nwy && (ni % 3) * 3 + nj % 3 < col) {
                         const int *p = done_cur + ni * plan.dg + nj;
-                        ok = (SPLIT ? ld_acquire_sys(p) : ld_acquire(p)) >= stamp;
+                        ok = (SPLIT ? ld_relaxed_sys(p) : ld_relaxed(p)) >= stamp;
                     }
                 }
                 for (int q = lane; q < pn; q += 32) {  // every window of the previous sweep within 64 px
                     const int *p = done_prev + (pi0 + q / pw) * plan.dg + pj0 + q % pw;
-                    ok = ok && (SPLIT ? ld_acquire_sys(p) : ld_acquire(p)) >= stamp - 1;
+                    ok = ok && (SPLIT ? ld_relaxed_sys(p) : ld_relaxed(p)) >= stamp - 1;
                 }
-                if (__all_sync(MPP_FULL, ok)) break;
+                if (__all_sync(MPP_FULL, ok)) {
+                    // polls are relaxed loads (see ld_relaxed: an acquire per poll empties the L1 of the SM each time); across
+                    // GPUs one acquire at the end of the wait keeps the formal ordering with the neighbour's release
+                    if (SPLIT && lane == 0) (void)ld_acquire_sys(done_cur + wi * plan.dg + wj);
+                    break;
+                }
                 __nanosleep(SPLIT ? 200 : 100);
                 // watchdog: a dependency that never completes (a neighbour rank that did not launch, bands of one device that are
                 // not co-resident) must end as an error, not as a hung GPU: ~4 s at 2 GHz (30 s across ranks, which start at different times)
@@ -142,8 +152,7 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
                 if (sc.done_up && x0 < sc.notify_lo) st_release_sys(sc.done_up + idx, stamp);
                 if (sc.done_down && x1 > sc.notify_hi) st_release_sys(sc.done_down + idx, stamp);
             } else {
-                __threadfence();
-                st_release(sc.done + idx, stamp);
+                st_release(sc.done + idx, stamp);  // (one MEMBAR: see k_windows_dataflow)
             }
         }
     }

@@ -379,9 +379,11 @@ __device__ __noinline__ void philox2(uint64_t seed, uint32_t c1, uint32_t c2, ui
 
 __device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float *n0, float *n1) {
     const float u1 = u01f(a), u2 = u01f(b);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    // hardware square root and sine / cosine on an argument reduced to [-pi, pi): absolute error < 1e-6 on a standard normal
+    // draw, i.e. 1e-5 px / 1e-6 of a mark range after scaling -- the IEEE sqrtf + sincospif cost ~70 instructions and a slow-path call
+    const float r = r_sqrt_fast(-2.0f * __logf(u1));
     float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
+    __sincosf(3.14159265358979f * (2.0f * u2 - (u2 >= 0.5f ? 2.0f : 0.0f)), &sn, &cs);
     *n0 = r * cs; *n1 = r * sn;
 }
 
@@ -554,7 +556,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             box_muller_f(q0.w, q1.x, &d0, &d1);
             nv = (pid == 0 ? w.size[r] : (pid == 1 ? w.ratio[r] : w.angle[r])) + (R)(d0 * (float)c.k.trf_sigma[pid]);
             const R vmax = (R)mark_vmax(pid);
-            if (pid == 2) { nv = nv - r_floor(nv / vmax) * vmax; if (!(nv < vmax) || nv < 0) nv = 0; }
+            if (pid == 2) { nv = nv - r_floor(nv * (R)(1.0 / 3.14159265358979323846)) * vmax; if (!(nv < vmax) || nv < 0) nv = 0; }
             else nv = r_min(r_max(nv, (R)0), vmax);
             ncls = value_to_class<R>(pid, nv);
             s = warp_sum(v);
@@ -607,7 +609,7 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
             if (a.size == w.size[r] && a.ratio == w.ratio[r]) {  // a translation or an angle transform keeps the half extents
                 a.hl = w.hl[r]; a.hw = w.hw[r];
             } else {
-                const R length = ((R)2 * a.size) / ((R)1 + a.ratio);
+                const R length = r_div_nocheck((R)2 * a.size, (R)1 + a.ratio);
                 a.hl = length / (R)2; a.hw = a.ratio * length / (R)2;
             }
             if (a.angle == w.angle[r]) {
@@ -1336,6 +1338,11 @@ __device__ __forceinline__ void simt_rounds(const Ctx<R> &c, WinState<R> &w, int
     }
 }
 
+// release store of an occupancy mask (publication of a visit: records first, then masks)
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // barrier among the `n_threads` (a multiple of 32) threads of the warps that stage a visit (named barrier 1; barrier 0 is
 // __syncthreads)
 __device__ __forceinline__ void stage_sync(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
@@ -1399,8 +1406,11 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         const double inv_total = c.cell_cdf[c.ncell];  // [ncell] = 1 / total mass
         int cell0 = 0, cell1 = 0;
         uint32_t msk0 = 0, msk1 = 0;
-        if (lane < ncells) { cell0 = (sy0 + lane % ncw) + (sx0 + lane / ncw) * c.ny; msk0 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell0)); }
-        if (lane + 32 < ncells) { cell1 = (sy0 + (lane + 32) % ncw) + (sx0 + (lane + 32) / ncw) * c.ny; msk1 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell1)); }
+        // (lane / ncw by multiply-shift: ncw <= 6 and lane + 32 < 72, exact with ceil(65536 / ncw))
+        const int rcw = ncw == 1 ? 65536 : (ncw == 2 ? 32768 : (ncw == 3 ? 21846 : (ncw == 4 ? 16384 : (ncw == 5 ? 13108 : 10923))));
+        const int q0r = (lane * rcw) >> 16, q1r = ((lane + 32) * rcw) >> 16;
+        if (lane < ncells) { cell0 = (sy0 + lane - q0r * ncw) + (sx0 + q0r) * c.ny; msk0 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell0)); }
+        if (lane + 32 < ncells) { cell1 = (sy0 + (lane + 32) - q1r * ncw) + (sx0 + q1r) * c.ny; msk1 = ld_state<SPLIT>(mask_ptr<SPLIT>(c, cell1)); }
         // per-visit constants, spread over the lanes
         if (lane < 8) w.pkf[lane] = c.k.pf[lane];
         for (int k = lane; k < MPP_WINDOW_STATS; k += 32) w.kstat[k] = 0;
@@ -1647,8 +1657,12 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
     if (threadIdx.x == 0) {
         if (w.masks_dirty) {
             // records before masks: a window staging these cells must never see a mask bit without its record
-            if (SPLIT) __threadfence_system(); else __threadfence();
-            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
+            if (SPLIT) {
+                __threadfence_system();
+                for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
+            } else {  // release stores: ordered after the records without the L1 invalidation a __threadfence() brings along
+                for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) st_release_u32(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
+            }
         }
         int n_done = w.n_done, n_acc = w.n_acc, n_birth = w.n_birth, n_death = w.n_death, n_eval = w.n_eval;
         if (!SIMT) {  // warp-per-proposal mode: the counters are sums of the per-kernel tallies
@@ -1698,6 +1712,18 @@ struct SweepPlan {
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polling load of a completion stamp.  Not an acquire: ld.acquire (and every fence) is followed by a CCTL.IVALL that empties the
+// SM's whole L1, i.e. the map lines (detection rows, row prefix sums, mark rows) that the proposals of BOTH resident CTAs keep
+// re-reading -- once per poll of a waiting CTA.  Acquire ordering is not needed here: everything the visit reads after the wait
+// that another visit may have written (occupancy masks, records) is read through L2 (__ldcg / ld.volatile), the coherence
+// point, by loads that are issued after the stamp has been seen (same warp: control dependency; other warps: barrier), and the
+// writer makes its stores visible at L2 before the stamp (MEMBAR of st.release).  L1 only ever holds the maps, which no
+// kernel writes.
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v) {
@@ -1771,10 +1797,10 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
                 if (lane < 25) {  // same sweep, earlier colours, |dwi|, |dwj| <= 2
                     const int ni = wi + lane / 5 - 2, nj = wj + lane % 5 - 2;
                     if (ni >= 0 && nj >= 0 && ni < nwx && nj < nwy && (ni % 3) * 3 + nj % 3 < col)
-                        ok = ld_acquire(done_cur + ni * plan.dg + nj) >= s + 1;
+                        ok = ld_relaxed(done_cur + ni * plan.dg + nj) >= s + 1;
                 }
                 for (int q = lane; q < pn; q += 32)  // every window of the previous sweep within 64 px
-                    ok = ok && ld_acquire(done_prev + (pi0 + q / pw) * plan.dg + pj0 + q % pw) >= s;
+                    ok = ok && ld_relaxed(done_prev + (pi0 + q / pw) * plan.dg + pj0 + q % pw) >= s;
                 if (__all_sync(MPP_FULL, ok)) break;
                 __nanosleep(100);
             }
@@ -1784,9 +1810,8 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
         window_visit<R, NW, DBG, SIMT>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
                                  uid_base + (uint32_t)t * (uint32_t)per_visit, dbg_maxdiff);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            st_release(plan.done + (size_t)(s & 1) * plan.dg * plan.dg + wi * plan.dg + wj, s + 1);
-        }
+        // (st.release orders every store of the CTA before the stamp -- the barrier above makes them thread 0's -- with one MEMBAR;
+        // a __threadfence() in front of it was a second, sequentially consistent one plus an L1 invalidation)
+        if (threadIdx.x == 0) st_release(plan.done + (size_t)(s & 1) * plan.dg * plan.dg + wi * plan.dg + wj, s + 1);
     }
 }
