@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
         plan.ox = sox; plan.oy = soy; plan.wi_lo = slo; plan.wi_hi = shi; plan.task_base = sbase; plan.temp = s_temp;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);
     for (;;) {
-        if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);
-        __syncthreads();
+        __syncthreads();  // s_task is set; the previous visit's statistics have been read out of `w` / `sc`
         const int t = s_task;
         if (t >= plan.total_tasks) break;
         // decode (sweep, colour, scene, window)
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
             }
         }
         window_visit<R, NW, DBG, false, SPLIT>(sc.c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], sc.seed, sweep_offset + (uint64_t)s, 0u, dbg_maxdiff);
+        if (threadIdx.x == 32 % (32 * NW)) s_task = atomicAdd(plan.next_task, 1);  // (see k_windows_dataflow)
         __syncthreads();
         if (threadIdx.x == 0) {
             const size_t idx = (size_t)(stamp & 1) * gsz + (size_t)wi * plan.dg + wj;
@@ -155,5 +156,6 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
                 st_release(sc.done + idx, stamp);  // (one MEMBAR: see k_windows_dataflow)
             }
         }
+        visit_statistics<R, NW, false>(sc.c, w, per_visit);
     }
 }

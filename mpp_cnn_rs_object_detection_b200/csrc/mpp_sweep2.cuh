@@ -903,7 +903,7 @@ __device__ __noinline__ void predraw_births(const Ctx<R> &c, WinState<R> &w, int
         if (birth) {
             float detv, pn[3], dm[3];
             gather_pixel(c, x, y, cls, &detv, pn, dm);
-            const R length = ((R)2 * size) / ((R)1 + ratio);
+            const R length = r_div_nocheck((R)2 * size, (R)1 + ratio);
             float fs, fc;
             __sincosf((float)angle, &fs, &fc);
             w.pc_x[hyp][it] = x; w.pc_y[hyp][it] = y; w.pc_cls[hyp][it] = cls;
@@ -1649,21 +1649,30 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         }
     }
 #endif
+    // publication of the state: the occupancy masks of the window's cells (the records were written by the commits).  The
+    // visit's statistics follow in visit_statistics, AFTER the caller has released the visit's completion stamp: the MEMBAR of a
+    // release waits for every outstanding store and atomic of the thread, and the dependents of this visit need not wait for
+    // forty statistics atomics.
+    if (threadIdx.x == 0 && w.masks_dirty) {
+        // records before masks: a window staging these cells must never see a mask bit without its record
+        if (SPLIT) {
+            __threadfence_system();
+            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
+        } else {  // release stores: ordered after the records without the L1 invalidation a __threadfence() brings along
+            for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) st_release_u32(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
+        }
+    }
+}
+
+// Adds the tallies of the visit that just ended to the context's counters (whole CTA; `w` must still hold the visit).
+template <typename R, int NW, bool SIMT = false>
+__device__ __forceinline__ void visit_statistics(const Ctx<R> &c, const WinState<R> &w, int per_visit) {
     if (!SIMT)  // (the per-kernel statistics are kept by the warp-per-proposal mode only)
         for (int k = threadIdx.x; k < MPP_WINDOW_STATS; k += 32 * NW) {
             const int v = k == 33 ? 1 : w.kstat[k];
             if (v) atomicAdd(c.kstats + k, (unsigned long long)v);
         }
     if (threadIdx.x == 0) {
-        if (w.masks_dirty) {
-            // records before masks: a window staging these cells must never see a mask bit without its record
-            if (SPLIT) {
-                __threadfence_system();
-                for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) __stcg(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
-            } else {  // release stores: ordered after the records without the L1 invalidation a __threadfence() brings along
-                for (int q = 0; q < 4; ++q) if (w.ccell[q] >= 0) st_release_u32(mask_ptr<SPLIT>(c, w.ccell[q]), w.cmask[q]);
-            }
-        }
         int n_done = w.n_done, n_acc = w.n_acc, n_birth = w.n_birth, n_death = w.n_death, n_eval = w.n_eval;
         if (!SIMT) {  // warp-per-proposal mode: the counters are sums of the per-kernel tallies
             n_done = per_visit; n_eval = 0; n_acc = 0;
@@ -1691,6 +1700,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep2(Ctx<R> c, int ci, int cj, in
     if (a >= n_wi * n_wj) return;
     window_visit<R, NW, DBG, SIMT>(c, w, scratch, ci + 3 * (a / n_wj), cj + 3 * (a % n_wj), ox, oy, per_visit, temp, seed, sweep_id,
                              uid_base + (uint32_t)a * (uint32_t)per_visit, dbg_maxdiff);
+    visit_statistics<R, NW, SIMT>(c, w, per_visit);
 }
 
 // ---- schedule 1: persistent dataflow kernel -------------------------------------------------------------
@@ -1760,9 +1770,9 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
         plan.ox = s_plan; plan.oy = s_plan + PLAN_S; plan.task_base = s_plan + 2 * PLAN_S; plan.temp = s_temp;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);
     for (;;) {
-        if (threadIdx.x == 0) s_task = atomicAdd(plan.next_task, 1);
-        __syncthreads();
+        __syncthreads();  // s_task is set; the previous visit's statistics have been read out of `w`
         const int t = s_task;
         if (t >= plan.total_tasks) break;
         // decode (sweep, colour, window)
@@ -1809,9 +1819,13 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_dataflow
         // is still waiting; window_visit's first barrier comes after warp 0 has staged the neighbourhood
         window_visit<R, NW, DBG, SIMT>(c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], seed, sweep_offset + (uint64_t)s,
                                  uid_base + (uint32_t)t * (uint32_t)per_visit, dbg_maxdiff);
+        // the next task is claimed while thread 0 publishes the masks (a global atomic with a return value is a ~1 us round trip;
+        // claimed any earlier, a ready task could sit behind a long visit while other CTAs are idle)
+        if (threadIdx.x == 32 % (32 * NW)) s_task = atomicAdd(plan.next_task, 1);
         __syncthreads();
         // (st.release orders every store of the CTA before the stamp -- the barrier above makes them thread 0's -- with one MEMBAR;
         // a __threadfence() in front of it was a second, sequentially consistent one plus an L1 invalidation)
         if (threadIdx.x == 0) st_release(plan.done + (size_t)(s & 1) * plan.dg * plan.dg + wi * plan.dg + wj, s + 1);
+        visit_statistics<R, NW, SIMT>(c, w, per_visit);
     }
 }
