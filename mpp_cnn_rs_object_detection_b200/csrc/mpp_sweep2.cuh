@@ -276,6 +276,7 @@ __device__ MPP_DELTA_INL R delta_staged(const ModelDev &m, const WinState<R> &w,
     const int rx = r >= 0 ? w.x[r] : 0, ry = r >= 0 ? w.y[r] : 0;
     R acc = 0, ov_add = 0, al_add = 0;
     const int n = w.n;
+#pragma unroll 1
     for (int k = lane; k < n; k += 32) {
         R o = 0, al = 0;
         if (k != r && (w.flags[k] & W2_ALIVE)) {
@@ -322,6 +323,7 @@ __device__ R delta_brute(const ModelDev &m, const WinState<R> &w, int r, bool ha
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
     R acc = 0;
     const int n = w.n;
+#pragma unroll 1
     for (int k = lane; k < n; k += 32) {
         if (!(w.flags[k] & W2_ALIVE)) continue;
         R ob = 0, ab = 0, oa = 0, aa = 0;
@@ -371,7 +373,17 @@ __device__ R delta_brute(const ModelDev &m, const WinState<R> &w, int r, bool ha
 
 // out-of-line copies of the two most replicated warp primitives of the sampler (instruction-cache footprint: with many
 // windows resident per SM the kernel is instruction-fetch bound, not issue bound)
-__device__ __noinline__ int warp_pick_ni(float w, float u, int lane, float *total_out) { return warp_pick(w, u, lane, total_out); }
+struct PickTotal { int idx; float total; };  // (by value, in registers: an out-pointer to an out-of-line function goes through the local stack)
+__device__ __noinline__ PickTotal warp_pick_nv(float w, float u, int lane) {
+    PickTotal o;
+    o.idx = warp_pick(w, u, lane, &o.total);
+    return o;
+}
+__device__ __forceinline__ int warp_pick_ni(float w, float u, int lane, float *total_out) {
+    const PickTotal o = warp_pick_nv(w, u, lane);
+    if (total_out) *total_out = o.total;
+    return o.idx;
+}
 __device__ __noinline__ void philox2(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, uint4 *q0, uint4 *q1) {
     Philox rng(seed, c1, c2, c3);
     *q0 = rng.next(); *q1 = rng.next();
@@ -399,6 +411,7 @@ __device__ __forceinline__ float pk_of(const WinState<R> &w, int kernel, int n) 
 template <typename R>
 __device__ __forceinline__ int pick_window_object(const WinState<R> &w, int j, int lane) {
     const int n = w.n;
+#pragma unroll 1
     for (int b = 0; b < n; b += 32) {
         const int k = b + lane;
         const bool in = k < n && (w.flags[k] & (W2_ALIVE | W2_WIN)) == (W2_ALIVE | W2_WIN);
@@ -665,6 +678,9 @@ template <typename R, bool SPLIT = false>
 __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &e, int it, int lane, R *sx, R *sy, const R *po, const R *pa) {
     const ModelDev &m = c.m;
     const int r = e.r;
+#ifdef MPP_TRACE
+    const long long tc0 = clock64();  // (instrumented build: phases of a commit, tools/visit_timers.py)
+#endif
     if (r >= 0 && lane == 0) {
         w.flags[r] = 0;
         const uint32_t h = w.handle[r];
@@ -678,6 +694,7 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         s = r;
         if (s < 0) {
             const int n = w.n;
+#pragma unroll 1
             for (int b = 0; b < n && s < 0; b += 32) {
                 const uint32_t bal = __ballot_sync(MPP_FULL, b + lane < n && !(w.flags[b + lane] & W2_ALIVE));
                 if (bal) s = b + __ffs(bal) - 1;
@@ -722,6 +739,10 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
     R n_o1 = 0, n_o2 = 0, n_a1 = 0, n_a2 = 0;
     int n_ao = -1, n_aa = -1, n_ao2 = -1, n_aa2 = -1;
     bool any_pair = false;
+#ifdef MPP_TRACE
+    const long long tc1 = clock64();
+#endif
+#pragma unroll 1
     for (int k = lane; k < n; k += 32) {
         if (k == s || !(w.flags[k] & W2_ALIVE)) continue;
         // the removed object was this entry's best or second-best partner: its top-2 must be rescanned -- unless the object is
@@ -769,12 +790,20 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         if ((redo_ov || redo_al) && (w.flags[k] & W2_INNER)) recompute_top2(m, w, k, redo_ov, redo_al, sx, sy);
         if ((w.flags[k] & W2_INNER) && (w.ov1[k] != o1_old || w.al1[k] != a1_old)) w.fcur[k] = f_obj(m, w, k, w.ov1[k], w.al1[k]);
     }
+#ifdef MPP_TRACE
+    __syncwarp();
+    const long long tc2 = clock64();
+    if (lane == 0) { atomicAdd(c.kstats + 35, (unsigned long long)(tc1 - tc0)); atomicAdd(c.kstats + 36, (unsigned long long)(tc2 - tc1)); atomicAdd(c.kstats + 38, 1ull); }
+#endif
     if (s >= 0 && !__any_sync(MPP_FULL, any_pair)) {  // no partner within reach of the new object
         if (lane == 0) {
             w.ov1[s] = 0; w.ov2[s] = 0; w.al1[s] = 0; w.al2[s] = 0; w.aov[s] = -1; w.aov2[s] = -1; w.aal[s] = -1; w.aal2[s] = -1;
             w.fcur[s] = f_obj(m, w, s, (R)0, (R)0);
         }
         __syncwarp();
+#ifdef MPP_TRACE
+        if (lane == 0) atomicAdd(c.kstats + 37, (unsigned long long)(clock64() - tc2));
+#endif
         return;
     }
     if (s >= 0) {  // merge the per-lane top-2 of (po, pa) into the new object's reductions (ties: lowest lane first)
@@ -799,6 +828,9 @@ __device__ void commit_proposal(const Ctx<R> &c, WinState<R> &w, const Eval<R> &
         }
     }
     __syncwarp();
+#ifdef MPP_TRACE
+    if (lane == 0) atomicAdd(c.kstats + 37, (unsigned long long)(clock64() - tc2));
+#endif
 }
 
 // ================================================================================================ SIMT mode
@@ -1188,6 +1220,7 @@ __device__ __forceinline__ void fill_pairs(const ModelDev &m, const WinState<R> 
     Geo<R> ga; ga.x = a.x; ga.y = a.y; ga.hl = a.hl; ga.hw = a.hw; ga.ca = a.ca; ga.sa = a.sa;
     const R rad_a = r_sqrt_fast(a.hl * a.hl + a.hw * a.hw);
     const int n = w.n;
+#pragma unroll 1
     for (int k = lane; k < n; k += 32) {
         R o = 0, al = 0;
         if (k != r && (w.flags[k] & W2_ALIVE)) {
@@ -1205,6 +1238,7 @@ template <typename R>
 __device__ __forceinline__ void rebuild_winlist(WinState<R> &w, int lane) {
     const int n = w.n;
     int cnt = 0;
+#pragma unroll 1
     for (int b = 0; b < n; b += 32) {
         const int k = b + lane;
         const bool in = k < n && (w.flags[k] & (W2_ALIVE | W2_WIN)) == (W2_ALIVE | W2_WIN);
@@ -1463,6 +1497,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         // phase B (still warp 0: no barrier in between): canonical order (by pixel, then uid) so that the chain does not depend
         // on storage slot order
         // (branch-free: one 64-bit (pixel key, uid) comparison per pair, the entries read by broadcast)
+#pragma unroll 1
         for (int k = lane; k < n; k += 32) {
             const unsigned long long key = ((unsigned long long)(uint32_t)w.x[k] << 32) | (unsigned long long)w.uid[k];
             int rank = 0;
@@ -1542,6 +1577,7 @@ __device__ void window_visit(const Ctx<R> &c, WinState<R> &w, R *scratch, int wi
         // (per warp, in the pair-value stash, which is free until a commit)
         int *near = reinterpret_cast<int *>(po);
         int n_near = 0;
+#pragma unroll 1
         for (int b = 0; b < w.n; b += 32) {
             const int k = b + lane;
             const bool in = k < w.n && (w.flags[k] & (W2_ALIVE | W2_INNER)) == (W2_ALIVE | W2_INNER);

@@ -46,6 +46,9 @@ for nw, pv in ((8, 96),):
     _lib.check(eng.lib.mpp_window_stats(eng.ctx, raw))
     v = [int(x) for x in raw]
     names = ["uniform_birth", "uniform_death", "data_birth", "data_death", "gaussian_translation", "data_translation", "gaussian_transform", "data_transform"]
+    if v[38]:
+        print(f"  commits {v[38]}: removal + new entry {v[35] / v[38] / 1900:.2f} us | update of the neighbours' reductions {v[36] / v[38] / 1900:.2f} us | "
+              f"new object's reductions {v[37] / v[38] / 1900:.2f} us")
     print("  per-kernel evaluation time of the generic rounds (us, instrumented build): draw part | Delta-energy part | count")
     for k in range(8):
         if v[56 + k]:
