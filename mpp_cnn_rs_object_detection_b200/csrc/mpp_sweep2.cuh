@@ -586,11 +586,10 @@ __device__ void evaluate_proposal(const Ctx<R> &c, const WinState<R> &w, uint64_
         if (pid == 0) a.size = nv; else if (pid == 1) a.ratio = nv; else a.angle = nv;
         a.cls = (w.cls[r] & ~(0xffu << (8 * pid))) | ((uint32_t)ncls << (8 * pid));
         a.detv = w.detv[r];
-        // (selects, not pn[pid] = ...: a run-time index would put both small arrays on the local stack)
-        const float pn_new = __fdividef(pnew, s);  // (as gather_pixel normalises the staged probabilities)
-        const float dm_new = mark_energy_f32(m, pid, pnew);
-        pn[0] = pid == 0 ? pn_new : w.pn0[r]; pn[1] = pid == 1 ? pn_new : w.pn1[r]; pn[2] = pid == 2 ? pn_new : w.pn2[r];
-        dm[0] = pid == 0 ? dm_new : (float)w.dm0[r]; dm[1] = pid == 1 ? dm_new : (float)w.dm1[r]; dm[2] = pid == 2 ? dm_new : (float)w.dm2[r];
+        pn[0] = w.pn0[r]; pn[1] = w.pn1[r]; pn[2] = w.pn2[r];
+        dm[0] = (float)w.dm0[r]; dm[1] = (float)w.dm1[r]; dm[2] = (float)w.dm2[r];
+        pn[pid] = __fdividef(pnew, s);  // (as gather_pixel normalises the staged probabilities)
+        dm[pid] = mark_energy_f32(m, pid, pnew);
         e->has_add = true;
         break;
     }
