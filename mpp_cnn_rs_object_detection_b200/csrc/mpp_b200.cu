@@ -1518,7 +1518,7 @@ static int launch_dataflow(mpp_ctx *h, int n_sweeps, int per_visit, double t0, d
     const int per_colour = (((h->H + 63) / 32 + 2) / 3) * (((h->W + 63) / 32 + 2) / 3);
     const int cap_x4 = SIMT ? 8 : 2;  // grid <= cap/4 colour classes + 8
     const int grid = std::max(1, std::min(std::min(total, blocks_per_sm * h->num_sms), cap_x4 * per_colour / 4 + 8));
-    k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(d_ctx, plan, per_visit, seed, sweep_offset, uid_base, dbg);
+    k_windows_dataflow<R, NW, DBG, SIMT><<<grid, 32 * NW, smem, h->stream>>>(view, d_ctx, plan, per_visit, seed, sweep_offset, uid_base, dbg);
     CUDA_TRY(cudaGetLastError());
     return MPP_OK;
 }
@@ -1742,7 +1742,7 @@ static int launch_multi(mpp_ctx **ctxs, const uint64_t *seeds, int n, uint64_t g
     if (max_ctas > 0) grid = std::min<long long>(grid, max_ctas);
     grid = std::max<long long>(grid, 1);
     if (total > 0)
-        k_windows_multi<R, NW, DBG, SPLIT><<<(int)grid, 32 * NW, smem, h0->stream>>>(reinterpret_cast<const SceneDev<R> *>(d_base + off_scenes), plan, per_visit,
+        k_windows_multi<R, NW, DBG, SPLIT><<<(int)grid, 32 * NW, smem, h0->stream>>>(scenes[0], reinterpret_cast<const SceneDev<R> *>(d_base + off_scenes), plan, per_visit,
                                                                                     sweep_offset, dbg);
     CUDA_TRY(cudaGetLastError());
     for (int k = 0; k < n; ++k) {

@@ -52,7 +52,8 @@ __device__ __forceinline__ void st_release_sys(int *p, int v) {
 }
 
 template <typename R, int NW, bool DBG, bool SPLIT>
-__global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(const SceneDev<R> *__restrict__ scenes, MultiPlan plan, int per_visit,
+__global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(const __grid_constant__ SceneDev<R> scene0,
+                                                                            const SceneDev<R> *__restrict__ scenes, MultiPlan plan, int per_visit,
                                                                             uint64_t sweep_offset, float *dbg_maxdiff) {
     extern __shared__ __align__(16) unsigned char smem[];
     WinState<R> &w = *reinterpret_cast<WinState<R> *>(smem);
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(32 * NW, MPP_DF_MIN_BLOCKS) k_windows_multi(co
                 if (clock64() - t_wait > (SPLIT ? 60000000000LL : 8000000000LL)) { if (lane == 0) atomicOr(sc.c.err, ERRF_TIMEOUT); break; }
             }
         }
-        window_visit<R, NW, DBG, false, SPLIT>(sc.c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], sc.seed, sweep_offset + (uint64_t)s, 0u, dbg_maxdiff);
+        // a split scene runs alone on its rank: its context is also in the kernel's parameter bank (`scene0`), where the inlined
+        // code reads it as immediate constant operands (see k_windows_dataflow); a batch of tiles has one context per scene
+        if (SPLIT) window_visit<R, NW, DBG, false, SPLIT>(scene0.c, sc.c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], sc.seed, sweep_offset + (uint64_t)s, 0u, dbg_maxdiff);
+        else window_visit<R, NW, DBG, false, SPLIT>(sc.c, sc.c, w, scratch, wi, wj, ox, oy, per_visit, plan.temp[s], sc.seed, sweep_offset + (uint64_t)s, 0u, dbg_maxdiff);
         if (threadIdx.x == 32 % (32 * NW)) s_task = atomicAdd(plan.next_task, 1);  // (see k_windows_dataflow)
         __syncthreads();
         if (threadIdx.x == 0) {
