@@ -24,7 +24,8 @@ def outline(path):
             m = re.search(r'([A-Za-z_0-9]+)\s*\(', l)
             if m: st.append((i, m.group(1)))
     return st
-base = '/root/repo/mpp_cnn_rs_object_detection_b200/csrc/'
+import os
+base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'mpp_cnn_rs_object_detection_b200', 'csrc') + os.sep
 out = {n: outline(base + n) for n in ('mpp_sweep2.cuh', 'mpp_device.cuh', 'mpp_proposals.cuh', 'mpp_clip.cuh')}
 def fn_of(file, line):
     if file in out and out[file]:
